@@ -1,0 +1,237 @@
+/*
+ * swe_b200.h — C-ABI of the B200-native SWE_FVM time step (the drop-in boundary).
+ *
+ * Plain C: pointers, sizes, enums. No C++/torch types cross this boundary. All functions
+ * return 0 on success or a negative swe_status; none throws. The C++17 host API in
+ * include/swe/ (SpaceDisc / TimeDisc / Solvers::*) forwards to these entry points and
+ * re-raises errors as the reference's exception types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * upstream SWE_FVM tree):
+ *
+ *   swe_mesh                <- Topology ctor arguments + Domain geometry
+ *                              (include/TriangMesh.h:27-33, include/Bathymetry.h:14,
+ *                               pybind/Topology.cpp:12-30)
+ *   swe_create              <- SpaceDisc::SpaceDisc (include/SpaceDisc.h:24, src/SpaceDisc.cpp:4-13)
+ *   swe_set_state/get_state <- MUSCLObject::GetVolField (include/MUSCLObject.h:6-7); layout of
+ *                              Storage<3> (include/Includes.h:26-27): 3 x Nt column-major (w,u,v)
+ *   swe_step                <- Solvers::Euler/SSPRK2/SSPRK3 (include/Solvers.h:6-8, src/Solvers.cpp)
+ *                              with the Fluxer plug-in (include/SpaceDisc.h:22) selected by enum:
+ *                              Fluxes::HLL<W>/HLLC<W> (include/Fluxes.h:14,56),
+ *                              W in Wavespeeds::{Rusanov,Davis,Einfeldt} (src/Fluxes.cpp:5-26)
+ *   swe_cfl_dt              <- TimeDisc::CFLdt (include/TimeDisc.h:13)
+ *   swe_compute_interface_values <- SpaceDisc::ComputeInterfaceValues (src/SpaceDisc.cpp:33-52)
+ *   swe_compute_fluxes      <- SpaceDisc::ComputeFluxes (src/SpaceDisc.cpp:54-74)
+ *   swe_get_edge_states     <- SpaceDisc::GetEdgField (include/SpaceDisc.h:26), EdgeIndexer order
+ *                              (include/ValueField.h:70-75)
+ *   swe_get_sources         <- SpaceDisc::GetSrcField (include/SpaceDisc.h:27)
+ *   swe_get_fluxes          <- SpaceDisc::GetFluxes (include/SpaceDisc.h:28)
+ *   swe_get_min_len_to_wavespeed <- SpaceDisc::GetMinLenToWavespeed (include/SpaceDisc.h:31)
+ *   swe_get_node_max_w      <- MUSCLObject::m_max_wp (include/MUSCLObject.h:68)
+ *   swe_get_draining_dt     <- TimeDisc::ComputeDrainingDt (src/TimeDisc.cpp:43-66)
+ *   swe_hostmesh_struct     <- StructTriangMesh(ni,nj,h) (include/StructTriangMesh.h:4-15; body
+ *                              missing upstream, conventions of notebooks/topology.dat)
+ *   swe_hostmesh_gmsh       <- TriangMesh(filename) Gmsh reader (examples/Main.cpp:174; body missing)
+ *   swe_case_*              <- Test::{b,u,v,h} (examples/Tests.h:20-27) + the IC loops of
+ *                              examples/Main.cpp:202-223,317-337 (TriangAverage,
+ *                              include/PointOperations.h:20-44)
+ */
+#ifndef SWE_B200_H
+#define SWE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SWE_API
+#else
+#define SWE_API __attribute__((visibility("default")))
+#endif
+
+typedef enum swe_status {
+    SWE_OK = 0,
+    SWE_ERR_INVALID = -1,   /* bad argument / unsupported mesh (DomainError upstream)   */
+    SWE_ERR_CUDA = -2,      /* CUDA runtime failure, incl. "no device"                  */
+    SWE_ERR_IO = -3,        /* mesh file could not be read (MeshError upstream)         */
+    SWE_ERR_NUMERIC = -4,   /* non-finite state detected on device (SolverError)        */
+    SWE_ERR_NOMEM = -5
+} swe_status;
+
+typedef enum swe_scheme { SWE_EULER = 0, SWE_SSPRK2 = 1, SWE_SSPRK3 = 2 } swe_scheme;
+typedef enum swe_flux { SWE_HLL = 0, SWE_HLLC = 1 } swe_flux;
+typedef enum swe_wavespeed { SWE_RUSANOV = 0, SWE_DAVIS = 1, SWE_EINFELDT = 2 } swe_wavespeed;
+
+/* Boundaries enum of include/Includes.h:21. Only SOLID_WALL is implemented upstream
+ * (src/SpaceDisc.cpp:66-72); swe_create rejects the others. */
+enum { SWE_SOLID_WALL = -1, SWE_FREE_FLOW = -2, SWE_PERIODIC = -3, SWE_CUSTOM = -4 };
+
+/* Mesh + bathymetry exactly as the reference's Topology/Domain take them. All arrays are
+ * HOST pointers, copied during swe_create (the caller may free them right after). */
+typedef struct swe_mesh {
+    int64_t nn, ne, nt;
+    const double *geometry;             /* 3 x nn column-major: (x, y, b) per node        */
+    const int64_t *edge_nodes;          /* ne x 2 row-major, EdgePoints                    */
+    const int64_t *edge_elements;       /* ne x 2 row-major, EdgeTriangs; [1] < 0 = wall   */
+    const int64_t *element_nodes;       /* nt x 3 row-major, TriangPoints (CCW)            */
+    const int64_t *element_edges;       /* nt x 3 row-major, TriangEdges                   */
+    const int64_t *element_neighbours;  /* nt x 3 row-major, TriangTriangs; < 0 = boundary */
+    double cor;                         /* Coriolis parameter (SpaceDisc ctor)             */
+    double tau;                         /* friction parameter: accepted, unused upstream   */
+} swe_mesh;
+
+/* ------------------------------------------------------------------------------------ */
+/* Device context = SpaceDisc + TimeDisc state on one GPU                                */
+/* ------------------------------------------------------------------------------------ */
+typedef struct swe_ctx swe_ctx;
+
+/* reorder: 0 = keep caller numbering on device, 1 = locality-preserving (Morton) renumbering
+ * of cells/edges/nodes on device. Results and every get/set use the CALLER's numbering. */
+SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reorder);
+SWE_API void swe_destroy(swe_ctx *ctx);
+/* message of the last failure on ctx (ctx may be NULL: last failure of swe_create/hostmesh). */
+SWE_API const char *swe_last_error(const swe_ctx *ctx);
+
+/* run all work of ctx on this cudaStream_t (default: the legacy default stream 0). */
+SWE_API int swe_set_stream(swe_ctx *ctx, void *cuda_stream);
+SWE_API int swe_synchronize(swe_ctx *ctx);
+
+/* Primitive state (w,u,v), 3 x nt column-major, caller numbering. HOST buffers.
+ * swe_set_state stores the values verbatim (use swe_case_initial_state or the C++
+ * PrimAssigner mirror to apply the dry clamp first). */
+SWE_API int swe_set_state(swe_ctx *ctx, const double *prim_3xnt);
+SWE_API int swe_get_state(swe_ctx *ctx, double *prim_3xnt);
+/* same, asynchronous on the ctx stream (buffers should be pinned). */
+SWE_API int swe_set_state_async(swe_ctx *ctx, const double *prim_3xnt);
+SWE_API int swe_get_state_async(swe_ctx *ctx, double *prim_3xnt);
+
+/* One time step of the chosen scheme with a fixed dt (like every reference driver). */
+SWE_API int swe_step(swe_ctx *ctx, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt);
+/* nsteps steps without host synchronisation. dt > 0: fixed dt. dt <= 0: adaptive, every
+ * step uses dt = CFLdt() of the previous step's last stage (device-resident, no read-back);
+ * the first adaptive step uses dt0. */
+SWE_API int swe_run(swe_ctx *ctx, swe_scheme scheme, swe_flux flux, swe_wavespeed ws,
+                    int64_t nsteps, double dt, double dt0);
+/* 0.15 * min(1, min over edges of length/wavespeed) of the last flux evaluation. */
+SWE_API int swe_cfl_dt(swe_ctx *ctx, double *dt);
+SWE_API int swe_get_min_len_to_wavespeed(swe_ctx *ctx, double *v);
+/* simulated time accumulated by swe_step/swe_run since the last swe_set_state. */
+SWE_API int swe_get_time(swe_ctx *ctx, double *t);
+/* number of kernels launched by this ctx so far (bench.py's gpu_launches). */
+SWE_API int64_t swe_launch_count(const swe_ctx *ctx);
+
+/* The two halves of a stage, callable on their own (parity taps, custom TimeDisc loops). */
+SWE_API int swe_compute_interface_values(swe_ctx *ctx);
+SWE_API int swe_compute_fluxes(swe_ctx *ctx, swe_flux flux, swe_wavespeed ws);
+/* stage update: cons(i) = a0*U0.cons(i) + a1*cons(i) + RHS(i, dt_stage), U0 = state saved by
+ * swe_save_state(). Euler: a0=0,a1=1. Uses the fluxes of the last swe_compute_fluxes. */
+SWE_API int swe_save_state(swe_ctx *ctx);
+SWE_API int swe_stage_update(swe_ctx *ctx, double a0, double a1, double dt_stage);
+
+/* Parity taps. HOST output buffers, caller numbering, reference layouts. */
+SWE_API int swe_get_edge_states(swe_ctx *ctx, double *edg_3x2ne); /* col = 2e + (from<to)  */
+SWE_API int swe_get_sources(swe_ctx *ctx, double *src_3x2ne);     /* row 0 is zero (unused) */
+SWE_API int swe_get_fluxes(swe_ctx *ctx, double *f_3xne);
+SWE_API int swe_get_node_max_w(swe_ctx *ctx, double *maxw_nn);
+SWE_API int swe_get_draining_dt(swe_ctx *ctx, double *dti_nt);    /* of the last stage      */
+SWE_API int swe_get_cell_class(swe_ctx *ctx, int8_t *cls_nt);     /* 0 dry 1 part 2 full    */
+
+/* Device reductions (diagnostics; the commented ComputeIntegrals of src/SpaceDisc.cpp:77-104):
+ * out[0] = sum A_i h_i (mass), out[1] = sum A_i 0.5 h (u^2+v^2), out[2] = sum A_i (0.5 h^2 + h b),
+ * out[3] = max |u|,|v|, out[4] = min h, out[5] = number of wet cells. Deterministic
+ * (fixed-shape tree). */
+SWE_API int swe_diagnostics(swe_ctx *ctx, double out[6]);
+
+/* ------------------------------------------------------------------------------------ */
+/* Multi-GPU support: a rank owns a sub-mesh with halo cells   */
+/* ------------------------------------------------------------------------------------ */
+/* CFL min only over edges with cfl_mask[e] != 0 (edges touching an owned cell). NULL = all. */
+SWE_API int swe_set_cfl_edge_mask(swe_ctx *ctx, const uint8_t *mask_ne);
+/* Register gather/scatter lists (caller numbering of local cells). */
+SWE_API int swe_halo_set_lists(swe_ctx *ctx, int64_t nsend, const int64_t *send_cells,
+                               int64_t nrecv, const int64_t *recv_cells);
+/* pack: sendbuf[c*nsend + k] = prim[c] of send_cells[k] (3 x nsend, component-major);
+ * unpack: the inverse into recv_cells. Buffers are DEVICE pointers (peer or NCCL buffers). */
+SWE_API int swe_halo_pack(swe_ctx *ctx, double *dev_sendbuf);
+SWE_API int swe_halo_unpack(swe_ctx *ctx, const double *dev_recvbuf);
+/* replace the running min_len_to_wavespeed (after the global min all-reduce). */
+SWE_API int swe_set_min_len_to_wavespeed(swe_ctx *ctx, double v);
+/* device address of the fp64 scalar holding min_len_to_wavespeed (for in-place NCCL all-reduce). */
+SWE_API int swe_min_len_device_ptr(swe_ctx *ctx, void **dev_ptr);
+
+/* ------------------------------------------------------------------------------------ */
+/* Host-side mesh construction (no GPU needed)                                            */
+/* ------------------------------------------------------------------------------------ */
+typedef struct swe_hostmesh swe_hostmesh;
+
+/* StructTriangMesh(ni, nj, h): [0,ni*h] x [0,nj*h], every square split by both diagonals
+ * into Bottom/Right/Top/Left triangles around a centre node; 4*ni*nj cells. i0/j0 shift
+ * the block inside a larger global grid (node coordinates are (i0+i)*h, bitwise equal to
+ * the global mesh), which is how a rank builds its strip of a larger grid directly. */
+SWE_API int swe_hostmesh_struct(swe_hostmesh **out, int64_t ni, int64_t nj, double h,
+                                int64_t i0, int64_t j0);
+/* Gmsh ASCII 4.1/4.2 reader reproducing the reference's numbering (notebooks/topology.dat). */
+SWE_API int swe_hostmesh_gmsh(swe_hostmesh **out, const char *path);
+/* build from raw triangles (+ optional boundary line list), same numbering rules. */
+SWE_API int swe_hostmesh_from_triangles(swe_hostmesh **out, int64_t nn, const double *xy_2xnn,
+                                        int64_t nt, const int64_t *tri_ntx3,
+                                        int64_t nb, const int64_t *bnd_nbx2);
+/* uniform 1 -> 4 refinement (edge midpoints); bathymetry of new nodes = mean of the ends. */
+SWE_API int swe_hostmesh_refine(swe_hostmesh **out, const swe_hostmesh *in);
+SWE_API void swe_hostmesh_free(swe_hostmesh *m);
+/* borrow views into m (valid until free); cor/tau are left 0. geometry is writable through
+ * swe_hostmesh_geometry so the caller can set the nodal bathymetry (row 2). */
+SWE_API int swe_hostmesh_view(const swe_hostmesh *m, swe_mesh *view);
+SWE_API double *swe_hostmesh_geometry(swe_hostmesh *m);
+
+/* Sub-mesh extraction for domain decomposition: cells with part[i] == rank plus `layers`
+ * rings of vertex-adjacent halo cells, in increasing global id (orientation preserving).
+ * Outputs (malloc'ed inside the returned hostmesh, borrowed): global ids of local cells,
+ * owner rank of each local cell. */
+SWE_API int swe_hostmesh_extract(swe_hostmesh **out, const swe_hostmesh *global,
+                                 const int32_t *part_nt, int32_t rank, int32_t layers);
+SWE_API const int64_t *swe_hostmesh_global_cells(const swe_hostmesh *m); /* nt, or NULL */
+SWE_API const int32_t *swe_hostmesh_cell_owner(const swe_hostmesh *m);   /* nt, or NULL */
+/* recursive coordinate bisection of cell centroids into nparts (any nparts >= 1). */
+SWE_API int swe_partition_rcb(const swe_hostmesh *m, int32_t nparts, int32_t *part_nt);
+
+/* ------------------------------------------------------------------------------------ */
+/* Analytic test cases (examples/Tests.h) — bathymetry and initial conditions             */
+/* ------------------------------------------------------------------------------------ */
+typedef enum swe_case_kind {
+    SWE_CASE_LAKE_AT_REST = 0,    /* LakeAtRestTest, examples/Tests.h:32-43                 */
+    SWE_CASE_CLASSIC_THACKER = 1, /* ClassicThackerTest, examples/Tests.h:237-280           */
+    SWE_CASE_GAUSS_WAVE = 2,      /* testGaussWave, examples/Main.cpp:172-195 (flat bed)    */
+    SWE_CASE_FULLY_WET = 3,       /* synthetic fully-wet variant               */
+    SWE_CASE_BOWL_HUMP = 4        /* BowlTest bed (examples/Tests.h:46-57) + Gaussian hump  */
+} swe_case_kind;
+
+typedef struct swe_case {
+    int32_t kind;
+    double mid_x, mid_y; /* centre of the domain feature                                   */
+    double length;       /* domain side l (FULLY_WET bed wavelength)                       */
+    double cor, tau;     /* [Common] cor, tau                                              */
+    double delta;        /* [Common] delta                                                 */
+    double H0, p0, q0;   /* [Thacker]                                                      */
+    double level, amp;   /* BOWL_HUMP still-water level; Gaussian hump amplitude           */
+} swe_case;
+
+SWE_API void swe_case_defaults(swe_case *c, int32_t kind, double mid_x, double mid_y, double length);
+/* exact solution at a point: out = (b, h, u, v). */
+SWE_API int swe_case_eval(const swe_case *c, double x, double y, double t, double out[4]);
+/* nodal bathymetry: geometry row 2 <- case.b(x,y). */
+SWE_API int swe_case_set_bathymetry(const swe_case *c, swe_hostmesh *m);
+/* cell initial state like examples/Main.cpp:211-223: (h,u,v) averaged by TriangAverage<3,n>
+ * at time t, then w = h_avg + b_i, then the PrimAssigner dry clamp. GAUSS_WAVE instead
+ * samples w at the centroid like examples/Main.cpp:183-186. out: 3 x nt column-major. */
+SWE_API int swe_case_initial_state(const swe_case *c, const swe_hostmesh *m, int32_t quad_n,
+                                   double t, double *prim_3xnt);
+
+SWE_API const char *swe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWE_B200_H */
