@@ -129,6 +129,14 @@ SWE_API int swe_compute_fluxes(swe_ctx *ctx, swe_flux flux, swe_wavespeed ws);
  * swe_save_state(). Euler: a0=0,a1=1. Uses the fluxes of the last swe_compute_fluxes. */
 SWE_API int swe_save_state(swe_ctx *ctx);
 SWE_API int swe_stage_update(swe_ctx *ctx, double a0, double a1, double dt_stage);
+/* same with dt_stage = coef * (device-resident dt): lets a multi-GPU driver step with the
+ * globally reduced CFL dt without reading it back. swe_set_dt stores dt on the device;
+ * swe_advance_dt does time += dt and, if adaptive, dt = 0.15 * min_len_to_wavespeed. */
+SWE_API int swe_stage_update_dev(swe_ctx *ctx, double a0, double a1, double coef);
+SWE_API int swe_set_dt(swe_ctx *ctx, double dt);
+SWE_API int swe_advance_dt(swe_ctx *ctx, int adaptive, double dt_fixed);
+/* keep the reconstructed edge-side w as well (needed only by swe_get_edge_states). */
+SWE_API int swe_enable_taps(swe_ctx *ctx, int on);
 
 /* Parity taps. HOST output buffers, caller numbering, reference layouts. */
 SWE_API int swe_get_edge_states(swe_ctx *ctx, double *edg_3x2ne); /* col = 2e + (from<to)  */

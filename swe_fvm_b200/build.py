@@ -1,0 +1,45 @@
+"""In-tree build of libswe_b200.so (nvcc, sm_100a only). The .so is git-ignored but travels
+to the GPU box with the working tree."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB = os.path.join(_HERE, "libswe_b200.so")
+SOURCES = ["swe_b200.cu", "hostmesh.cpp"]
+HEADERS = ["swe_kernels.cuh", "swe_device.cuh", "hostmesh.hpp", os.path.join("..", "..", "include", "swe_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",            # bit parity with the CPU oracle (g++ -ffp-contract=off)
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
+    "-shared", "-cudart", "static",
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    if os.path.exists("/usr/bin/g++"):
+        cmd += ["-ccbin", "/usr/bin/g++"]
+    cmd += ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    build_lib(force=True, verbose="-v" in sys.argv)
+    print(LIB)

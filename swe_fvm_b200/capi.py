@@ -83,6 +83,10 @@ SYMBOLS = {
     "swe_compute_fluxes": (C.c_int, [_P, C.c_int, C.c_int]),
     "swe_save_state": (C.c_int, [_P]),
     "swe_stage_update": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "swe_stage_update_dev": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "swe_set_dt": (C.c_int, [_P, C.c_double]),
+    "swe_advance_dt": (C.c_int, [_P, C.c_int, C.c_double]),
+    "swe_enable_taps": (C.c_int, [_P, C.c_int]),
     "swe_get_edge_states": (C.c_int, [_P, _D]),
     "swe_get_sources": (C.c_int, [_P, _D]),
     "swe_get_fluxes": (C.c_int, [_P, _D]),

@@ -1,0 +1,700 @@
+// swe_b200.cu — device context and C-ABI entry points of include/swe_b200.h.
+//
+// A swe_ctx is the device-resident equivalent of the reference's SpaceDisc + TimeDisc
+// (include/SpaceDisc.h:20-48, include/TimeDisc.h:4-23): mesh topology and precomputed geometry
+// uploaded once as structure-of-arrays (optionally Morton-renumbered), the cell state, the
+// edge-side reconstructions, fluxes, node maxima and draining time steps. Every C function
+// returns a status; nothing throws across the boundary. There is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/swe_b200.h"
+#include "hostmesh.hpp"
+#include "swe_kernels.cuh"
+
+using namespace swe;
+
+struct swe_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    std::string err;
+    int64_t launches = 0;
+    int nt = 0, ne = 0, nn = 0;
+    double cor = 0, tau = 0;
+    bool reordered = false;
+    bool taps = false;
+    // device mesh
+    int *tt = nullptr, *te = nullptr, *tp = nullptr, *slotL = nullptr, *slotR = nullptr;
+    double4 *cgeo = nullptr, *node = nullptr;
+    double2 *en = nullptr;
+    double *area = nullptr, *elen = nullptr, *dmin = nullptr;
+    unsigned char *cfl_mask = nullptr;
+    int *cell_old = nullptr, *edge_old = nullptr, *node_old = nullptr;  // device id -> caller id
+    std::vector<int> cell_new;  // caller id -> device id (host; halo lists)
+    // fields
+    double *bufA[3] = {nullptr, nullptr, nullptr}, *bufB[3] = {nullptr, nullptr, nullptr};
+    double **cur = nullptr, **sav = nullptr;  // point at bufA / bufB
+    double *ceh = nullptr, *ceu = nullptr, *cev = nullptr, *csx = nullptr, *csy = nullptr, *cew = nullptr;
+    double *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *maxw = nullptr, *dti = nullptr;
+    signed char *cls = nullptr;
+    double *scal = nullptr;
+    int *flags = nullptr;
+    double *diag = nullptr;  // partials + 6 outputs
+    double *stage_aos = nullptr;  // 3*max(nt, 2ne) staging for host transfers
+    size_t stage_cap = 0;
+    // halo
+    int *send_cells = nullptr, *recv_cells = nullptr;
+    int nsend = 0, nrecv = 0;
+    bool saved_pending = false;
+};
+
+static thread_local std::string g_create_error;
+
+#define CUDA_TRY(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return SWE_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+
+static DevMesh dev_mesh(const swe_ctx *c) {
+    DevMesh m;
+    m.nt = c->nt; m.ne = c->ne; m.nn = c->nn;
+    m.tt = c->tt; m.te = c->te; m.tp = c->tp;
+    m.cgeo = c->cgeo; m.area = c->area; m.node = c->node;
+    m.slotL = c->slotL; m.slotR = c->slotR; m.en = c->en; m.elen = c->elen; m.dmin = c->dmin;
+    m.cfl_mask = c->cfl_mask;
+    return m;
+}
+static DevFields dev_fields(const swe_ctx *c) {
+    DevFields s;
+    s.w = c->cur[0]; s.u = c->cur[1]; s.v = c->cur[2];
+    s.ceh = c->ceh; s.ceu = c->ceu; s.cev = c->cev; s.csx = c->csx; s.csy = c->csy; s.cew = c->cew;
+    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.maxw = c->maxw; s.dti = c->dti; s.cls = c->cls;
+    s.scal = c->scal; s.flags = c->flags;
+    return s;
+}
+
+template <class T>
+static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+static int launch_check(swe_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { c->err = std::string(what) + ": " + cudaGetErrorString(e); return SWE_ERR_CUDA; }
+    c->launches++;
+    return SWE_OK;
+}
+
+// Morton key of a point in the unit square (21 bits per axis)
+static inline uint64_t spread21(uint64_t x) {
+    x &= 0x1fffff;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+static void morton_order(const std::vector<double> &x, const std::vector<double> &y, double x0, double y0,
+                         double sx, double sy, std::vector<int> &newid) {
+    const size_t n = x.size();
+    std::vector<std::pair<uint64_t, int>> keys(n);
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t qx = (uint64_t)std::min(2097151.0, std::max(0.0, (x[i] - x0) * sx));
+        uint64_t qy = (uint64_t)std::min(2097151.0, std::max(0.0, (y[i] - y0) * sy));
+        keys[i] = {spread21(qx) | (spread21(qy) << 1), (int)i};
+    }
+    std::sort(keys.begin(), keys.end());
+    newid.resize(n);
+    for (size_t k = 0; k < n; ++k) newid[keys[k].second] = (int)k;
+}
+
+static void destroy_ctx(swe_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    void *ptrs[] = {c->tt, c->te, c->tp, c->slotL, c->slotR, c->cgeo, c->node, c->en, c->area, c->elen, c->dmin,
+                    c->cfl_mask, c->cell_old, c->edge_old, c->node_old, c->bufA[0], c->bufA[1], c->bufA[2],
+                    c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->csx, c->csy, c->cew, c->f0, c->f1,
+                    c->f2, c->maxw, c->dti, c->cls, c->scal, c->flags, c->diag, c->stage_aos, c->send_cells,
+                    c->recv_cells};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete c;
+}
+
+static int ensure_stage(swe_ctx *c, size_t n_doubles) {
+    if (c->stage_cap >= n_doubles) return SWE_OK;
+    if (c->stage_aos) cudaFree(c->stage_aos);
+    c->stage_aos = nullptr; c->stage_cap = 0;
+    CUDA_TRY(c, dalloc(&c->stage_aos, n_doubles));
+    c->stage_cap = n_doubles;
+    return SWE_OK;
+}
+
+template <int FLUX>
+static void launch_flux_ws(swe_ctx *c, const DevMesh &m, const DevFields &s, int ws) {
+    const int g = nblk(c->ne, kBlock);
+    const double ac = std::fabs(c->cor);
+    switch (ws) {
+        case SWE_RUSANOV: k_flux<FLUX, WS_RUSANOV><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
+        case SWE_DAVIS: k_flux<FLUX, WS_DAVIS><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
+        default: k_flux<FLUX, WS_EINFELDT><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
+    }
+}
+
+extern "C" {
+
+SWE_API const char *swe_version(void) { return "swe_b200 0.1 (sm_100a, fp64, -fmad=false)"; }
+
+SWE_API const char *swe_last_error(const swe_ctx *ctx) {
+    if (ctx) return ctx->err.c_str();
+    if (!g_create_error.empty()) return g_create_error.c_str();
+    return swe::host_error();
+}
+
+SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reorder) {
+    g_create_error.clear();
+    auto fail = [&](int code, const std::string &msg) { g_create_error = msg; return code; };
+    if (!out || !mesh) return fail(SWE_ERR_INVALID, "swe_create: null argument");
+    *out = nullptr;
+    const int64_t nn = mesh->nn, ne = mesh->ne, nt = mesh->nt;
+    if (nn <= 0 || ne <= 0 || nt <= 0 || !mesh->geometry || !mesh->edge_nodes || !mesh->edge_elements ||
+        !mesh->element_nodes || !mesh->element_edges || !mesh->element_neighbours)
+        return fail(SWE_ERR_INVALID, "swe_create: empty mesh or null array");
+    if (3 * nt >= (int64_t)2147483647 || 2 * ne >= (int64_t)2147483647)
+        return fail(SWE_ERR_INVALID, "swe_create: mesh too large for int32 device ids");
+    // validate ids and boundary tags (only SOLID_WALL is implemented upstream, src/SpaceDisc.cpp:66-72)
+    for (int64_t e = 0; e < ne; ++e) {
+        const int64_t a = mesh->edge_elements[2 * e], b = mesh->edge_elements[2 * e + 1];
+        if (a < 0 || a >= nt || b >= nt) return fail(SWE_ERR_INVALID, "swe_create: edge_elements id out of range");
+        if (b < 0 && b != SWE_SOLID_WALL)
+            return fail(SWE_ERR_INVALID, "swe_create: only SOLID_WALL (-1) boundaries are supported");
+        if (mesh->edge_nodes[2 * e] < 0 || mesh->edge_nodes[2 * e] >= nn || mesh->edge_nodes[2 * e + 1] < 0 ||
+            mesh->edge_nodes[2 * e + 1] >= nn)
+            return fail(SWE_ERR_INVALID, "swe_create: edge_nodes id out of range");
+    }
+    for (int64_t k = 0; k < 3 * nt; ++k) {
+        if (mesh->element_nodes[k] < 0 || mesh->element_nodes[k] >= nn)
+            return fail(SWE_ERR_INVALID, "swe_create: element_nodes id out of range");
+        if (mesh->element_edges[k] < 0 || mesh->element_edges[k] >= ne)
+            return fail(SWE_ERR_INVALID, "swe_create: element_edges id out of range");
+        const int64_t nb = mesh->element_neighbours[k];
+        if (nb >= nt || (nb < 0 && nb != SWE_SOLID_WALL))
+            return fail(SWE_ERR_INVALID, "swe_create: element_neighbours id out of range / unsupported boundary");
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(SWE_ERR_CUDA, std::string("swe_create: no CUDA device available (") +
+                                      (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") +
+                                      "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SWE_ERR_INVALID, "swe_create: bad device ordinal");
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(SWE_ERR_CUDA, cudaGetErrorString(ce));
+
+    swe_ctx *c = new (std::nothrow) swe_ctx();
+    if (!c) return fail(SWE_ERR_NOMEM, "out of host memory");
+    c->device = device; c->nt = (int)nt; c->ne = (int)ne; c->nn = (int)nn;
+    c->cor = mesh->cor; c->tau = mesh->tau;
+    c->reordered = reorder != 0;
+
+    // ---- numbering: caller id -> device id ----
+    std::vector<int> cell_new, edge_new, node_new;
+    try {
+        if (c->reordered) {
+            double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+            for (int64_t p = 0; p < nn; ++p) {
+                x0 = std::min(x0, mesh->geometry[3 * p]); x1 = std::max(x1, mesh->geometry[3 * p]);
+                y0 = std::min(y0, mesh->geometry[3 * p + 1]); y1 = std::max(y1, mesh->geometry[3 * p + 1]);
+            }
+            const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
+            const double sc = 2097152.0 / span;
+            std::vector<double> xs((size_t)nt), ys((size_t)nt);
+            for (int64_t t = 0; t < nt; ++t) {
+                const int64_t *q = &mesh->element_nodes[3 * t];
+                xs[t] = (mesh->geometry[3 * q[0]] + mesh->geometry[3 * q[1]] + mesh->geometry[3 * q[2]]) / 3.;
+                ys[t] = (mesh->geometry[3 * q[0] + 1] + mesh->geometry[3 * q[1] + 1] + mesh->geometry[3 * q[2] + 1]) / 3.;
+            }
+            morton_order(xs, ys, x0, y0, sc, sc, cell_new);
+            xs.resize((size_t)ne); ys.resize((size_t)ne);
+            for (int64_t e = 0; e < ne; ++e) {
+                const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
+                xs[e] = 0.5 * (mesh->geometry[3 * a] + mesh->geometry[3 * b]);
+                ys[e] = 0.5 * (mesh->geometry[3 * a + 1] + mesh->geometry[3 * b + 1]);
+            }
+            morton_order(xs, ys, x0, y0, sc, sc, edge_new);
+            xs.resize((size_t)nn); ys.resize((size_t)nn);
+            for (int64_t p = 0; p < nn; ++p) { xs[p] = mesh->geometry[3 * p]; ys[p] = mesh->geometry[3 * p + 1]; }
+            morton_order(xs, ys, x0, y0, sc, sc, node_new);
+        } else {
+            cell_new.resize((size_t)nt); std::iota(cell_new.begin(), cell_new.end(), 0);
+            edge_new.resize((size_t)ne); std::iota(edge_new.begin(), edge_new.end(), 0);
+            node_new.resize((size_t)nn); std::iota(node_new.begin(), node_new.end(), 0);
+        }
+    } catch (const std::bad_alloc &) { delete c; return fail(SWE_ERR_NOMEM, "out of host memory"); }
+    c->cell_new = cell_new;
+
+#define CREATE_TRY(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            std::string msg_ = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            destroy_ctx(c);                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? SWE_ERR_NOMEM : SWE_ERR_CUDA, msg_);    \
+        }                                                                                         \
+    } while (0)
+
+    // ---- host-side conversion to int32 SoA in device numbering ----
+    {
+        std::vector<int> h_tp((size_t)3 * nt), h_tt((size_t)3 * nt), h_te((size_t)3 * nt);
+        for (int64_t t = 0; t < nt; ++t) {
+            const int d = cell_new[t];
+            for (int k = 0; k < 3; ++k) {
+                h_tp[(size_t)k * nt + d] = node_new[mesh->element_nodes[3 * t + k]];
+                const int64_t nb = mesh->element_neighbours[3 * t + k];
+                h_tt[(size_t)k * nt + d] = nb >= 0 ? cell_new[nb] : (int)nb;
+                const int64_t e = mesh->element_edges[3 * t + k];
+                const bool first = mesh->edge_elements[2 * e] == t;
+                if (!first && mesh->edge_elements[2 * e + 1] != t) {
+                    destroy_ctx(c);
+                    return fail(SWE_ERR_INVALID, "swe_create: element_edges / edge_elements are inconsistent");
+                }
+                h_te[(size_t)k * nt + d] = first ? edge_new[e] : ~edge_new[e];
+            }
+        }
+        CREATE_TRY(dalloc(&c->tp, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->tt, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->te, (size_t)3 * nt));
+        CREATE_TRY(cudaMemcpy(c->tp, h_tp.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(c->tt, h_tt.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(c->te, h_te.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
+    }
+    int *d_ep0 = nullptr, *d_ep1 = nullptr, *d_et0 = nullptr, *d_et1 = nullptr;
+    {
+        std::vector<int> h((size_t)4 * ne);
+        int *ep0 = h.data(), *ep1 = ep0 + ne, *et0 = ep1 + ne, *et1 = et0 + ne;
+        for (int64_t e = 0; e < ne; ++e) {
+            const int d = edge_new[e];
+            ep0[d] = node_new[mesh->edge_nodes[2 * e]]; ep1[d] = node_new[mesh->edge_nodes[2 * e + 1]];
+            et0[d] = cell_new[mesh->edge_elements[2 * e]];
+            const int64_t b = mesh->edge_elements[2 * e + 1];
+            et1[d] = b >= 0 ? cell_new[b] : (int)b;
+        }
+        CREATE_TRY(dalloc(&d_ep0, (size_t)4 * ne));
+        d_ep1 = d_ep0 + ne; d_et0 = d_ep1 + ne; d_et1 = d_et0 + ne;
+        CREATE_TRY(cudaMemcpy(d_ep0, h.data(), sizeof(int) * 4 * ne, cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<double> h((size_t)4 * nn);
+        for (int64_t p = 0; p < nn; ++p) {
+            double *q = &h[(size_t)4 * node_new[p]];
+            q[0] = mesh->geometry[3 * p]; q[1] = mesh->geometry[3 * p + 1]; q[2] = mesh->geometry[3 * p + 2]; q[3] = 0.;
+        }
+        CREATE_TRY(dalloc(&c->node, (size_t)nn));
+        CREATE_TRY(cudaMemcpy(c->node, h.data(), sizeof(double) * 4 * nn, cudaMemcpyHostToDevice));
+    }
+    if (c->reordered) {
+        std::vector<int> inv((size_t)std::max(std::max(nt, ne), nn));
+        for (int64_t t = 0; t < nt; ++t) inv[cell_new[t]] = (int)t;
+        CREATE_TRY(dalloc(&c->cell_old, (size_t)nt));
+        CREATE_TRY(cudaMemcpy(c->cell_old, inv.data(), sizeof(int) * nt, cudaMemcpyHostToDevice));
+        for (int64_t e = 0; e < ne; ++e) inv[edge_new[e]] = (int)e;
+        CREATE_TRY(dalloc(&c->edge_old, (size_t)ne));
+        CREATE_TRY(cudaMemcpy(c->edge_old, inv.data(), sizeof(int) * ne, cudaMemcpyHostToDevice));
+        for (int64_t p = 0; p < nn; ++p) inv[node_new[p]] = (int)p;
+        CREATE_TRY(dalloc(&c->node_old, (size_t)nn));
+        CREATE_TRY(cudaMemcpy(c->node_old, inv.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
+    }
+    // ---- geometry on device ----
+    CREATE_TRY(dalloc(&c->cgeo, (size_t)nt)); CREATE_TRY(dalloc(&c->area, (size_t)nt));
+    CREATE_TRY(dalloc(&c->slotL, (size_t)ne)); CREATE_TRY(dalloc(&c->slotR, (size_t)ne));
+    CREATE_TRY(dalloc(&c->en, (size_t)ne)); CREATE_TRY(dalloc(&c->elen, (size_t)ne)); CREATE_TRY(dalloc(&c->dmin, (size_t)ne));
+    CREATE_TRY(cudaMemset(c->slotR, 0xff, sizeof(int) * ne));
+    CREATE_TRY(cudaMemset(c->slotL, 0xff, sizeof(int) * ne));
+    k_setup_cells<<<nblk(nt, 256), 256>>>(c->nt, c->tp, c->tt, c->node, c->cgeo, c->area);
+    k_setup_slots<<<nblk(nt, 256), 256>>>(c->nt, c->te, c->slotL, c->slotR);
+    k_setup_edges<<<nblk(ne, 256), 256>>>(c->ne, c->nt, d_ep0, d_ep1, d_et0, d_et1, c->node, c->cgeo, c->area, c->en,
+                                         c->elen, c->dmin);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaDeviceSynchronize());
+    cudaFree(d_ep0);
+    c->launches += 3;
+    // ---- fields ----
+    for (int q = 0; q < 3; ++q) { CREATE_TRY(dalloc(&c->bufA[q], (size_t)nt)); CREATE_TRY(dalloc(&c->bufB[q], (size_t)nt)); }
+    c->cur = c->bufA; c->sav = c->bufA;
+    CREATE_TRY(dalloc(&c->ceh, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->ceu, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->cev, (size_t)3 * nt));
+    CREATE_TRY(dalloc(&c->csx, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->csy, (size_t)3 * nt));
+    CREATE_TRY(dalloc(&c->f0, (size_t)ne)); CREATE_TRY(dalloc(&c->f1, (size_t)ne)); CREATE_TRY(dalloc(&c->f2, (size_t)ne));
+    CREATE_TRY(dalloc(&c->maxw, (size_t)nn)); CREATE_TRY(dalloc(&c->dti, (size_t)nt)); CREATE_TRY(dalloc(&c->cls, (size_t)nt));
+    CREATE_TRY(dalloc(&c->scal, 8)); CREATE_TRY(dalloc(&c->flags, 4));
+    CREATE_TRY(dalloc(&c->diag, (size_t)6 * kDiagBlocks + 8));
+    for (int q = 0; q < 3; ++q) {
+        CREATE_TRY(cudaMemset(c->bufA[q], 0, sizeof(double) * nt));
+        CREATE_TRY(cudaMemset(c->bufB[q], 0, sizeof(double) * nt));
+    }
+    CREATE_TRY(cudaMemset(c->ceh, 0, sizeof(double) * 3 * nt)); CREATE_TRY(cudaMemset(c->ceu, 0, sizeof(double) * 3 * nt));
+    CREATE_TRY(cudaMemset(c->cev, 0, sizeof(double) * 3 * nt)); CREATE_TRY(cudaMemset(c->csx, 0, sizeof(double) * 3 * nt));
+    CREATE_TRY(cudaMemset(c->csy, 0, sizeof(double) * 3 * nt));
+    CREATE_TRY(cudaMemset(c->f0, 0, sizeof(double) * ne)); CREATE_TRY(cudaMemset(c->f1, 0, sizeof(double) * ne));
+    CREATE_TRY(cudaMemset(c->f2, 0, sizeof(double) * ne));
+    CREATE_TRY(cudaMemset(c->dti, 0, sizeof(double) * nt)); CREATE_TRY(cudaMemset(c->cls, 0, nt));
+    CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 4));
+    const double scal0[8] = {1.0, 0.0, 0.0, 0, 0, 0, 0, 0};
+    CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaDeviceSynchronize());
+#undef CREATE_TRY
+    *out = c;
+    return SWE_OK;
+}
+
+SWE_API void swe_destroy(swe_ctx *ctx) { destroy_ctx(ctx); }
+
+SWE_API int swe_set_stream(swe_ctx *c, void *stream) {
+    if (!c) return SWE_ERR_INVALID;
+    c->stream = (cudaStream_t)stream;
+    return SWE_OK;
+}
+
+SWE_API int swe_synchronize(swe_ctx *c) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int flag = 0;
+    CUDA_TRY(c, cudaMemcpy(&flag, c->flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) { c->err = "non-finite cell state detected on device (SolverError)"; return SWE_ERR_NUMERIC; }
+    return SWE_OK;
+}
+
+// ---- state transfer ----
+SWE_API int swe_set_state_async(swe_ctx *c, const double *prim) {
+    if (!c || !prim) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)3 * c->nt);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->stage_aos, prim, sizeof(double) * 3 * c->nt, cudaMemcpyHostToDevice, c->stream));
+    k_state_in<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, c->stage_aos, c->cur[0], c->cur[1], c->cur[2]);
+    if ((rc = launch_check(c, "k_state_in"))) return rc;
+    k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal + 2, 0.0);
+    CUDA_TRY(c, cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));
+    return launch_check(c, "k_set_scalar");
+}
+SWE_API int swe_set_state(swe_ctx *c, const double *prim) {
+    int rc = swe_set_state_async(c, prim);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+SWE_API int swe_get_state_async(swe_ctx *c, double *prim) {
+    if (!c || !prim) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)3 * c->nt);
+    if (rc) return rc;
+    k_state_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, c->cur[0], c->cur[1], c->cur[2], c->stage_aos);
+    if ((rc = launch_check(c, "k_state_out"))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(prim, c->stage_aos, sizeof(double) * 3 * c->nt, cudaMemcpyDeviceToHost, c->stream));
+    return SWE_OK;
+}
+SWE_API int swe_get_state(swe_ctx *c, double *prim) {
+    int rc = swe_get_state_async(c, prim);
+    if (rc) return rc;
+    return swe_synchronize(c);
+}
+
+// ---- the stage pieces ----
+SWE_API int swe_enable_taps(swe_ctx *c, int on) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (on && !c->cew) {
+        CUDA_TRY(c, dalloc(&c->cew, (size_t)3 * c->nt));
+        CUDA_TRY(c, cudaMemset(c->cew, 0, sizeof(double) * 3 * c->nt));
+    }
+    c->taps = on != 0;
+    return SWE_OK;
+}
+
+SWE_API int swe_compute_interface_values(swe_ctx *c) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const DevMesh m = dev_mesh(c);
+    const DevFields s = dev_fields(c);
+    int rc;
+    k_stage_begin<<<nblk(std::max(c->nn, 1), 256), 256, 0, c->stream>>>(m, s);
+    if ((rc = launch_check(c, "k_stage_begin"))) return rc;
+    if (c->taps) k_reconstruct<true><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
+    else k_reconstruct<false><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
+    if ((rc = launch_check(c, "k_reconstruct"))) return rc;
+    if (c->taps) k_partwet2<true><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
+    else k_partwet2<false><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
+    return launch_check(c, "k_partwet2");
+}
+
+SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {
+    if (!c) return SWE_ERR_INVALID;
+    if ((flux != SWE_HLL && flux != SWE_HLLC) || ws < SWE_RUSANOV || ws > SWE_EINFELDT) {
+        c->err = "swe_compute_fluxes: unknown flux / wavespeed (registered: HLL, HLLC x Rusanov, Davis, Einfeldt)";
+        return SWE_ERR_INVALID;
+    }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const DevMesh m = dev_mesh(c);
+    const DevFields s = dev_fields(c);
+    if (flux == SWE_HLL) launch_flux_ws<FLUX_HLL>(c, m, s, ws); else launch_flux_ws<FLUX_HLLC>(c, m, s, ws);
+    return launch_check(c, "k_flux");
+}
+
+SWE_API int swe_save_state(swe_ctx *c) {
+    if (!c) return SWE_ERR_INVALID;
+    c->sav = c->cur;  // no copy: the next stage update writes the other buffer
+    c->saved_pending = true;
+    return SWE_OK;
+}
+
+static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double dt_coef) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const DevMesh m = dev_mesh(c);
+    const DevFields s = dev_fields(c);
+    int rc;
+    k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+    if ((rc = launch_check(c, "k_drain"))) return rc;
+    double **outb = c->cur;
+    if (c->saved_pending && c->sav == c->cur) {  // first stage after save: keep U0 intact
+        outb = (c->cur == c->bufA) ? c->bufB : c->bufA;
+        c->saved_pending = false;
+    }
+    const int g = nblk(c->nt, kBlock);
+    if (a0 == 0.)
+        k_update<true><<<g, kBlock, 0, c->stream>>>(m, s, nullptr, nullptr, nullptr, outb[0], outb[1], outb[2], a0, a1,
+                                                    dt_host, dt_coef);
+    else
+        k_update<false><<<g, kBlock, 0, c->stream>>>(m, s, c->sav[0], c->sav[1], c->sav[2], outb[0], outb[1], outb[2],
+                                                     a0, a1, dt_host, dt_coef);
+    if ((rc = launch_check(c, "k_update"))) return rc;
+    c->cur = outb;
+    return SWE_OK;
+}
+
+SWE_API int swe_stage_update(swe_ctx *c, double a0, double a1, double dt_stage) {
+    if (!c) return SWE_ERR_INVALID;
+    if (a0 == 0. && a1 != 1.) { c->err = "swe_stage_update: a0 == 0 requires a1 == 1 (plain U + RHS)"; return SWE_ERR_INVALID; }
+    return stage_update(c, a0, a1, dt_stage, 0.);
+}
+// stage dt = coef * device-resident dt (set by swe_set_dt / swe_advance_dt)
+SWE_API int swe_stage_update_dev(swe_ctx *c, double a0, double a1, double coef) {
+    if (!c || coef == 0.) return SWE_ERR_INVALID;
+    return stage_update(c, a0, a1, 0., coef);
+}
+SWE_API int swe_set_dt(swe_ctx *c, double dt) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal + 1, dt);
+    return launch_check(c, "k_set_scalar");
+}
+// time += dt; if adaptive: dt = 0.15 * min_len_to_wavespeed (after the global min all-reduce)
+SWE_API int swe_advance_dt(swe_ctx *c, int adaptive, double dt_fixed) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_post_step<<<1, 1, 0, c->stream>>>(dev_fields(c), dt_fixed, adaptive);
+    return launch_check(c, "k_post_step");
+}
+
+static int one_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt, bool dev_dt) {
+    int rc;
+    auto upd = [&](double a0, double a1, double coef) {
+        return dev_dt ? stage_update(c, a0, a1, 0., coef) : stage_update(c, a0, a1, coef * dt, 0.);
+    };
+    if ((rc = swe_compute_interface_values(c))) return rc;
+    if ((rc = swe_compute_fluxes(c, flux, ws))) return rc;
+    if (scheme == SWE_EULER) return dev_dt ? stage_update(c, 0., 1., 0., 1.) : stage_update(c, 0., 1., dt, 0.);
+    swe_save_state(c);
+    // first stage: U0 + RHS(dt)
+    if ((rc = (dev_dt ? stage_update(c, 0., 1., 0., 1.) : stage_update(c, 0., 1., dt, 0.)))) return rc;
+    if ((rc = swe_compute_interface_values(c))) return rc;
+    if ((rc = swe_compute_fluxes(c, flux, ws))) return rc;
+    if (scheme == SWE_SSPRK2) return upd(0.5, 0.5, 0.5);
+    if ((rc = upd(0.75, 0.25, 0.25))) return rc;
+    if ((rc = swe_compute_interface_values(c))) return rc;
+    if ((rc = swe_compute_fluxes(c, flux, ws))) return rc;
+    return upd((1. / 3.), (2. / 3.), (2. / 3.));
+}
+
+SWE_API int swe_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt) {
+    if (!c) return SWE_ERR_INVALID;
+    if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { c->err = "swe_step: unknown scheme"; return SWE_ERR_INVALID; }
+    if (!(dt > 0.)) { c->err = "swe_step: dt must be positive"; return SWE_ERR_INVALID; }
+    int rc = one_step(c, scheme, flux, ws, dt, false);
+    if (rc) return rc;
+    return swe_advance_dt(c, 0, dt);
+}
+
+SWE_API int swe_run(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, int64_t nsteps, double dt, double dt0) {
+    if (!c) return SWE_ERR_INVALID;
+    if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { c->err = "swe_run: unknown scheme"; return SWE_ERR_INVALID; }
+    const bool adaptive = !(dt > 0.);
+    if (adaptive && !(dt0 > 0.)) { c->err = "swe_run: adaptive mode needs dt0 > 0"; return SWE_ERR_INVALID; }
+    int rc;
+    if (adaptive && (rc = swe_set_dt(c, dt0))) return rc;
+    for (int64_t s = 0; s < nsteps; ++s) {
+        if ((rc = one_step(c, scheme, flux, ws, dt, adaptive))) return rc;
+        if ((rc = swe_advance_dt(c, adaptive ? 1 : 0, dt))) return rc;
+    }
+    return SWE_OK;
+}
+
+static int read_scalar(swe_ctx *c, int idx, double *v) {
+    if (!c || !v) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(v, c->scal + idx, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+SWE_API int swe_get_min_len_to_wavespeed(swe_ctx *c, double *v) { return read_scalar(c, 0, v); }
+SWE_API int swe_cfl_dt(swe_ctx *c, double *dt) {
+    double v = 0;
+    int rc = read_scalar(c, 0, &v);
+    if (rc) return rc;
+    *dt = 0.15 * v;  // m_constCFL (include/TimeDisc.h:22)
+    return SWE_OK;
+}
+SWE_API int swe_get_time(swe_ctx *c, double *t) { return read_scalar(c, 2, t); }
+SWE_API int64_t swe_launch_count(const swe_ctx *c) { return c ? c->launches : 0; }
+SWE_API int swe_set_min_len_to_wavespeed(swe_ctx *c, double v) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal, v);
+    return launch_check(c, "k_set_scalar");
+}
+SWE_API int swe_min_len_device_ptr(swe_ctx *c, void **p) {
+    if (!c || !p) return SWE_ERR_INVALID;
+    *p = c->scal;
+    return SWE_OK;
+}
+
+// ---- taps ----
+static int tap_out(swe_ctx *c, double *host, size_t n_doubles) {
+    CUDA_TRY(c, cudaMemcpyAsync(host, c->stage_aos, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+static int edge_tap(swe_ctx *c, double *out, int which) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    if (which == 0 && !c->cew) { c->err = "swe_get_edge_states: call swe_enable_taps(ctx, 1) before computing"; return SWE_ERR_INVALID; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)6 * c->ne;
+    int rc = ensure_stage(c, std::max(n, (size_t)3 * c->nt));
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemsetAsync(c->stage_aos, 0, sizeof(double) * n, c->stream));
+    k_edge_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(dev_mesh(c), dev_fields(c), c->cell_old, c->edge_old, which, c->stage_aos);
+    if ((rc = launch_check(c, "k_edge_out"))) return rc;
+    return tap_out(c, out, n);
+}
+SWE_API int swe_get_edge_states(swe_ctx *c, double *out) { return edge_tap(c, out, 0); }
+SWE_API int swe_get_sources(swe_ctx *c, double *out) { return edge_tap(c, out, 1); }
+SWE_API int swe_get_fluxes(swe_ctx *c, double *out) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, std::max((size_t)3 * c->ne, (size_t)3 * c->nt));
+    if (rc) return rc;
+    k_flux_out<<<nblk(c->ne, 256), 256, 0, c->stream>>>(c->ne, c->edge_old, c->f0, c->f1, c->f2, c->stage_aos);
+    if ((rc = launch_check(c, "k_flux_out"))) return rc;
+    return tap_out(c, out, (size_t)3 * c->ne);
+}
+static int scalar_tap(swe_ctx *c, double *out, const double *src, int n, const int *old) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)3 * c->nt);
+    if (rc) return rc;
+    if ((size_t)n > c->stage_cap && (rc = ensure_stage(c, (size_t)n))) return rc;
+    k_scalar_out<<<nblk(n, 256), 256, 0, c->stream>>>(n, old, src, c->stage_aos);
+    if ((rc = launch_check(c, "k_scalar_out"))) return rc;
+    return tap_out(c, out, (size_t)n);
+}
+SWE_API int swe_get_node_max_w(swe_ctx *c, double *out) { return c ? scalar_tap(c, out, c->maxw, c->nn, c->node_old) : SWE_ERR_INVALID; }
+SWE_API int swe_get_draining_dt(swe_ctx *c, double *out) { return c ? scalar_tap(c, out, c->dti, c->nt, c->cell_old) : SWE_ERR_INVALID; }
+SWE_API int swe_get_cell_class(swe_ctx *c, int8_t *out) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)3 * c->nt);
+    if (rc) return rc;
+    k_cls_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, c->cls, (signed char *)c->stage_aos);
+    if ((rc = launch_check(c, "k_cls_out"))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->stage_aos, (size_t)c->nt, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+
+SWE_API int swe_diagnostics(swe_ctx *c, double out[6]) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_diag_partial<<<kDiagBlocks, kDiagThreads, 0, c->stream>>>(dev_mesh(c), dev_fields(c), c->diag);
+    int rc;
+    if ((rc = launch_check(c, "k_diag_partial"))) return rc;
+    k_diag_final<<<1, 32, 0, c->stream>>>(c->diag, c->diag + 6 * kDiagBlocks);
+    if ((rc = launch_check(c, "k_diag_final"))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->diag + 6 * kDiagBlocks, sizeof(double) * 6, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+
+// ---- multi-GPU support ----
+SWE_API int swe_set_cfl_edge_mask(swe_ctx *c, const uint8_t *mask) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!mask) {
+        if (c->cfl_mask) cudaFree(c->cfl_mask);
+        c->cfl_mask = nullptr;
+        return SWE_OK;
+    }
+    std::vector<unsigned char> h((size_t)c->ne);
+    if (c->reordered) {
+        std::vector<int> old((size_t)c->ne);
+        CUDA_TRY(c, cudaMemcpy(old.data(), c->edge_old, sizeof(int) * c->ne, cudaMemcpyDeviceToHost));
+        for (int d = 0; d < c->ne; ++d) h[d] = mask[old[d]];
+    } else {
+        std::copy(mask, mask + c->ne, h.begin());
+    }
+    if (!c->cfl_mask) CUDA_TRY(c, dalloc(&c->cfl_mask, (size_t)c->ne));
+    CUDA_TRY(c, cudaMemcpy(c->cfl_mask, h.data(), (size_t)c->ne, cudaMemcpyHostToDevice));
+    return SWE_OK;
+}
+
+SWE_API int swe_halo_set_lists(swe_ctx *c, int64_t nsend, const int64_t *send_cells, int64_t nrecv, const int64_t *recv_cells) {
+    if (!c || nsend < 0 || nrecv < 0 || (nsend && !send_cells) || (nrecv && !recv_cells)) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    auto upload = [&](int64_t n, const int64_t *src, int **dst) -> int {
+        if (*dst) { cudaFree(*dst); *dst = nullptr; }
+        if (n == 0) return SWE_OK;
+        std::vector<int> h((size_t)n);
+        for (int64_t k = 0; k < n; ++k) {
+            if (src[k] < 0 || src[k] >= c->nt) { c->err = "swe_halo_set_lists: cell id out of range"; return SWE_ERR_INVALID; }
+            h[k] = c->cell_new[src[k]];
+        }
+        CUDA_TRY(c, dalloc(dst, (size_t)n));
+        CUDA_TRY(c, cudaMemcpy(*dst, h.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        return SWE_OK;
+    };
+    int rc;
+    if ((rc = upload(nsend, send_cells, &c->send_cells))) return rc;
+    if ((rc = upload(nrecv, recv_cells, &c->recv_cells))) return rc;
+    c->nsend = (int)nsend; c->nrecv = (int)nrecv;
+    return SWE_OK;
+}
+SWE_API int swe_halo_pack(swe_ctx *c, double *buf) {
+    if (!c || (c->nsend && !buf)) return SWE_ERR_INVALID;
+    if (c->nsend == 0) return SWE_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_halo_pack<<<nblk(c->nsend, 256), 256, 0, c->stream>>>(c->nsend, c->send_cells, c->cur[0], c->cur[1], c->cur[2], buf);
+    return launch_check(c, "k_halo_pack");
+}
+SWE_API int swe_halo_unpack(swe_ctx *c, const double *buf) {
+    if (!c || (c->nrecv && !buf)) return SWE_ERR_INVALID;
+    if (c->nrecv == 0) return SWE_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_halo_unpack<<<nblk(c->nrecv, 256), 256, 0, c->stream>>>(c->nrecv, c->recv_cells, buf, c->cur[0], c->cur[1], c->cur[2]);
+    return launch_check(c, "k_halo_unpack");
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's SpaceDisc / TimeDisc / Solvers API over the C-ABI.
+
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0, cor=0, tau=0)   # include/SpaceDisc.h:24
+    td = TimeDisc(sd)                                              # include/TimeDisc.h:6
+    Solvers.SSPRK2(td, dt)                                         # include/Solvers.h:7
+    td.CFLdt()                                                     # include/TimeDisc.h:13
+
+The reference plugs the flux in as a std::function (include/SpaceDisc.h:22); a std::function
+cannot run on the device, so the known fluxers are selected by name from the compile-time
+registry {HLL, HLLC} x {Rusanov, Davis, Einfeldt} (include/Fluxes.h, src/Fluxes.cpp).
+All state lives in HBM; numpy arrays cross the boundary only in set/get calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .mesh import TriangMesh
+
+
+class SpaceDisc:
+    def __init__(self, flux: str | int, wavespeed: str | int, mesh: TriangMesh, v0: np.ndarray | None = None,
+                 cor: float = 0.0, tau: float = 0.0, device: int = 0, reorder: bool = False, taps: bool = False):
+        self.flux = capi.FLUXES[flux.lower()] if isinstance(flux, str) else int(flux)
+        self.wavespeed = capi.WAVESPEEDS[wavespeed.lower()] if isinstance(wavespeed, str) else int(wavespeed)
+        self.mesh = mesh
+        self.nt, self.ne, self.nn = mesh.nt, mesh.ne, mesh.nn
+        self.cor, self.tau = float(cor), float(tau)
+        self._ctx = C.c_void_p()
+        cm = mesh.c_mesh(cor, tau)
+        capi.check(capi.lib().swe_create(C.byref(self._ctx), C.byref(cm), device, int(reorder)))
+        if taps:
+            self._call("swe_enable_taps", 1)
+        if v0 is not None:
+            self.SetVolField(v0)
+
+    # -- plumbing --
+    def _call(self, name, *args):
+        capi.check(getattr(capi.lib(), name)(self._ctx, *args), self._ctx)
+
+    def _get(self, name, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        ptr = out.ctypes.data_as(C.POINTER(C.c_double if dtype == np.float64 else C.c_int8))
+        self._call(name, ptr)
+        return out
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._call("swe_set_stream", C.c_void_p(cuda_stream_ptr))
+
+    def synchronize(self):
+        self._call("swe_synchronize")
+
+    # -- reference accessors --
+    def SetVolField(self, prim):
+        p = capi.as_f64(prim, (self.nt, 3))
+        self._call("swe_set_state", capi.dptr(p))
+
+    def GetVolField(self) -> np.ndarray:
+        """(nt, 3) primitive (w, u, v), the layout of Storage<3>."""
+        return self._get("swe_get_state", (self.nt, 3))
+
+    def set_state_async(self, pinned_ptr: int):
+        self._call("swe_set_state_async", C.cast(C.c_void_p(pinned_ptr), C.POINTER(C.c_double)))
+
+    def get_state_async(self, pinned_ptr: int):
+        self._call("swe_get_state_async", C.cast(C.c_void_p(pinned_ptr), C.POINTER(C.c_double)))
+
+    def ComputeInterfaceValues(self):
+        self._call("swe_compute_interface_values")
+
+    def ComputeFluxes(self):
+        self._call("swe_compute_fluxes", self.flux, self.wavespeed)
+
+    def GetEdgField(self) -> np.ndarray:
+        return self._get("swe_get_edge_states", (2 * self.ne, 3))
+
+    def GetSrcField(self) -> np.ndarray:
+        return self._get("swe_get_sources", (2 * self.ne, 3))
+
+    def GetFluxes(self) -> np.ndarray:
+        return self._get("swe_get_fluxes", (self.ne, 3))
+
+    def GetMinLenToWavespeed(self) -> float:
+        v = C.c_double()
+        self._call("swe_get_min_len_to_wavespeed", C.byref(v))
+        return v.value
+
+    def GetCor(self):
+        return self.cor
+
+    def GetTau(self):
+        return self.tau
+
+    def node_max_w(self) -> np.ndarray:
+        return self._get("swe_get_node_max_w", (self.nn,))
+
+    def draining_dt(self) -> np.ndarray:
+        return self._get("swe_get_draining_dt", (self.nt,))
+
+    def cell_class(self) -> np.ndarray:
+        return self._get("swe_get_cell_class", (self.nt,), dtype=np.int8)
+
+    def diagnostics(self) -> dict:
+        out = self._get("swe_diagnostics", (6,))
+        return dict(mass=out[0], kinetic=out[1], potential=out[2], vmax=out[3], hmin=out[4], wet_cells=int(out[5]))
+
+    def time(self) -> float:
+        v = C.c_double()
+        self._call("swe_get_time", C.byref(v))
+        return v.value
+
+    def launch_count(self) -> int:
+        return int(capi.lib().swe_launch_count(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            capi.lib().swe_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TimeDisc:
+    def __init__(self, sd: SpaceDisc | None = None):
+        self._sd = sd
+
+    def GetSpaceDisc(self) -> SpaceDisc:
+        return self._sd
+
+    def SetSpaceDisc(self, sd: SpaceDisc):
+        self._sd = sd
+
+    def CFLdt(self) -> float:
+        v = C.c_double()
+        self._sd._call("swe_cfl_dt", C.byref(v))
+        return v.value
+
+
+class Solvers:
+    """Solvers::Euler / SSPRK2 / SSPRK3 (src/Solvers.cpp): one step of size dt on the device."""
+
+    @staticmethod
+    def _step(td: TimeDisc, scheme: int, dt: float):
+        sd = td.GetSpaceDisc()
+        sd._call("swe_step", scheme, sd.flux, sd.wavespeed, float(dt))
+
+    @staticmethod
+    def Euler(td: TimeDisc, dt: float):
+        Solvers._step(td, capi.EULER, dt)
+
+    @staticmethod
+    def SSPRK2(td: TimeDisc, dt: float):
+        Solvers._step(td, capi.SSPRK2, dt)
+
+    @staticmethod
+    def SSPRK3(td: TimeDisc, dt: float):
+        Solvers._step(td, capi.SSPRK3, dt)
+
+    @staticmethod
+    def run(td: TimeDisc, scheme: str | int, nsteps: int, dt: float = 0.0, dt0: float = 0.0):
+        """nsteps steps without host synchronisation; dt <= 0: dt = CFLdt() of the previous step."""
+        sd = td.GetSpaceDisc()
+        sc = capi.SCHEMES[scheme.lower()] if isinstance(scheme, str) else int(scheme)
+        sd._call("swe_run", sc, sd.flux, sd.wavespeed, int(nsteps), float(dt), float(dt0))
