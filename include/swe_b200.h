@@ -122,6 +122,14 @@ SWE_API int swe_get_time(swe_ctx *ctx, double *t);
 /* number of kernels launched by this ctx so far (bench.py's gpu_launches). */
 SWE_API int64_t swe_launch_count(const swe_ctx *ctx);
 
+/* Per-kernel timing with CUDA events on the ctx stream (bench.py's roofline numbers).
+ * swe_kernel_timing(ctx, 1) starts (and clears) the recording, swe_kernel_times returns the
+ * number of kernel kinds K (<= max_kinds) and fills total milliseconds, launch counts and
+ * static name strings per kind. */
+SWE_API int swe_kernel_timing(swe_ctx *ctx, int enable);
+SWE_API int swe_kernel_times(swe_ctx *ctx, int32_t max_kinds, double *ms_total, int64_t *counts,
+                             const char **names);
+
 /* The two halves of a stage, callable on their own (parity taps, custom TimeDisc loops). */
 SWE_API int swe_compute_interface_values(swe_ctx *ctx);
 SWE_API int swe_compute_fluxes(swe_ctx *ctx, swe_flux flux, swe_wavespeed ws);
@@ -160,8 +168,9 @@ SWE_API int swe_set_cfl_edge_mask(swe_ctx *ctx, const uint8_t *mask_ne);
 /* Register gather/scatter lists (caller numbering of local cells). */
 SWE_API int swe_halo_set_lists(swe_ctx *ctx, int64_t nsend, const int64_t *send_cells,
                                int64_t nrecv, const int64_t *recv_cells);
-/* pack: sendbuf[c*nsend + k] = prim[c] of send_cells[k] (3 x nsend, component-major);
- * unpack: the inverse into recv_cells. Buffers are DEVICE pointers (peer or NCCL buffers). */
+/* pack: sendbuf[3k + c] = prim[c] of send_cells[k] (Storage<3> layout, so each peer's
+ * segment is contiguous); unpack: the inverse into recv_cells. Buffers are DEVICE pointers
+ * (NCCL or peer-mapped buffers). */
 SWE_API int swe_halo_pack(swe_ctx *ctx, double *dev_sendbuf);
 SWE_API int swe_halo_unpack(swe_ctx *ctx, const double *dev_recvbuf);
 /* replace the running min_len_to_wavespeed (after the global min all-reduce). */

@@ -15,8 +15,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # bit parity with the CPU oracle (g++ -ffp-contract=off)
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
-    "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2,-fopenmp",
+    "-shared", "-cudart", "static", "-lgomp",
 ]
 
 
@@ -27,7 +27,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def build_variant(out: str, defines: list[str], verbose: bool = False) -> str:
+    """Tuning builds: same sources with extra -D flags, written to `out`."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    if os.path.exists("/usr/bin/g++"):
+        cmd += ["-ccbin", "/usr/bin/g++"]
+    cmd += ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    if os.environ.get("SWE_B200_LIB"):
+        return os.environ["SWE_B200_LIB"]
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

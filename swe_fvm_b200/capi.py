@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswe_b200.so")
+# SWE_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SWE_B200_LIB") or os.path.join(_HERE, "libswe_b200.so")
 
 OK = 0
 EULER, SSPRK2, SSPRK3 = 0, 1, 2
@@ -79,6 +80,8 @@ SYMBOLS = {
     "swe_get_min_len_to_wavespeed": (C.c_int, [_P, _D]),
     "swe_get_time": (C.c_int, [_P, _D]),
     "swe_launch_count": (C.c_int64, [_P]),
+    "swe_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "swe_kernel_times": (C.c_int, [_P, C.c_int32, _D, _I64, C.POINTER(C.c_char_p)]),
     "swe_compute_interface_values": (C.c_int, [_P]),
     "swe_compute_fluxes": (C.c_int, [_P, C.c_int, C.c_int]),
     "swe_save_state": (C.c_int, [_P]),

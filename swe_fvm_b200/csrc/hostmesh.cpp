@@ -525,6 +525,8 @@ static void triang_average(const double *p0, const double *p1, const double *p2,
 
 void case_initial_state(const swe_case &c, const swe_hostmesh &m, int quad_n, double t, double *prim) {
     const double third = 1. / 3.;
+    // the reference's IC loop carries `#pragma omp parallel for` too (examples/Main.cpp:210)
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < m.nt; ++i) {
         const double *p0 = &m.geom[3 * m.tp[3 * i]], *p1 = &m.geom[3 * m.tp[3 * i + 1]], *p2 = &m.geom[3 * m.tp[3 * i + 2]];
         // VolumeDomainWrapper::At = Domain::T(i)[2] (src/ValueField.cpp:8-10, src/Bathymetry.cpp:24-27)
@@ -679,8 +681,9 @@ SWE_API int swe_case_eval(const swe_case *c, double x, double y, double t, doubl
 
 SWE_API int swe_case_set_bathymetry(const swe_case *c, swe_hostmesh *m) {
     if (!c || !m || c->kind < 0 || c->kind > SWE_CASE_BOWL_HUMP) { set_host_error("swe_case_set_bathymetry: bad argument"); return SWE_ERR_INVALID; }
-    double o[4];
+#pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < m->nn; ++p) {
+        double o[4];
         swe::case_eval(*c, m->geom[3 * p], m->geom[3 * p + 1], 0., o);
         m->geom[3 * p + 2] = o[0];
     }

@@ -25,6 +25,7 @@ struct swe_ctx {
     std::string err;
     int64_t launches = 0;
     int nt = 0, ne = 0, nn = 0;
+    int sms = 148;
     double cor = 0, tau = 0;
     bool reordered = false;
     bool taps = false;
@@ -32,16 +33,18 @@ struct swe_ctx {
     int *tt = nullptr, *te = nullptr, *tp = nullptr, *slotL = nullptr, *slotR = nullptr;
     double4 *cgeo = nullptr, *node = nullptr;
     double2 *en = nullptr;
-    double *area = nullptr, *elen = nullptr, *dmin = nullptr;
+    double *area = nullptr, *cb = nullptr, *elen = nullptr, *dmin = nullptr;
+    int *n2c_start = nullptr, *n2c_cells = nullptr;
     unsigned char *cfl_mask = nullptr;
     int *cell_old = nullptr, *edge_old = nullptr, *node_old = nullptr;  // device id -> caller id
     std::vector<int> cell_new;  // caller id -> device id (host; halo lists)
     // fields
     double *bufA[3] = {nullptr, nullptr, nullptr}, *bufB[3] = {nullptr, nullptr, nullptr};
     double **cur = nullptr, **sav = nullptr;  // point at bufA / bufB
-    double *ceh = nullptr, *ceu = nullptr, *cev = nullptr, *csx = nullptr, *csy = nullptr, *cew = nullptr;
-    double *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *maxw = nullptr, *dti = nullptr;
+    double *ceh = nullptr, *ceu = nullptr, *cev = nullptr, *cgx = nullptr, *cgy = nullptr, *cew = nullptr;
+    double *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *dti = nullptr;
     signed char *cls = nullptr;
+    int *pw_list = nullptr;
     double *scal = nullptr;
     int *flags = nullptr;
     double *diag = nullptr;  // partials + 6 outputs
@@ -51,7 +54,30 @@ struct swe_ctx {
     int *send_cells = nullptr, *recv_cells = nullptr;
     int nsend = 0, nrecv = 0;
     bool saved_pending = false;
+    // optional per-kernel CUDA-event timing (bench.py roofline): pairs recorded on c->stream
+    bool ktiming = false;
+    struct KtPair { cudaEvent_t a, b; int id; };
+    std::vector<KtPair> kt_pairs;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_pool;
 };
+
+enum { KT_RECONSTRUCT = 0, KT_PARTWET2, KT_FLUX, KT_DRAIN, KT_UPDATE, KT_COUNT };
+static const char *kt_names[KT_COUNT] = {"k_reconstruct", "k_partwet2", "k_flux", "k_drain", "k_update"};
+constexpr size_t kKtMaxPairs = 8192;
+
+static inline int kt_begin(swe_ctx *c, int id) {
+    if (!c->ktiming || c->kt_pairs.size() >= kKtMaxPairs) return -1;
+    swe_ctx::KtPair p;
+    if (!c->kt_pool.empty()) { p.a = c->kt_pool.back().first; p.b = c->kt_pool.back().second; c->kt_pool.pop_back(); }
+    else { if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1; }
+    p.id = id;
+    cudaEventRecord(p.a, c->stream);
+    c->kt_pairs.push_back(p);
+    return (int)c->kt_pairs.size() - 1;
+}
+static inline void kt_end(swe_ctx *c, int h) {
+    if (h >= 0) cudaEventRecord(c->kt_pairs[h].b, c->stream);
+}
 
 static thread_local std::string g_create_error;
 
@@ -70,7 +96,8 @@ static DevMesh dev_mesh(const swe_ctx *c) {
     DevMesh m;
     m.nt = c->nt; m.ne = c->ne; m.nn = c->nn;
     m.tt = c->tt; m.te = c->te; m.tp = c->tp;
-    m.cgeo = c->cgeo; m.area = c->area; m.node = c->node;
+    m.cgeo = c->cgeo; m.area = c->area; m.cb = c->cb; m.node = c->node;
+    m.n2c_start = c->n2c_start; m.n2c_cells = c->n2c_cells;
     m.slotL = c->slotL; m.slotR = c->slotR; m.en = c->en; m.elen = c->elen; m.dmin = c->dmin;
     m.cfl_mask = c->cfl_mask;
     return m;
@@ -78,8 +105,8 @@ static DevMesh dev_mesh(const swe_ctx *c) {
 static DevFields dev_fields(const swe_ctx *c) {
     DevFields s;
     s.w = c->cur[0]; s.u = c->cur[1]; s.v = c->cur[2];
-    s.ceh = c->ceh; s.ceu = c->ceu; s.cev = c->cev; s.csx = c->csx; s.csy = c->csy; s.cew = c->cew;
-    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.maxw = c->maxw; s.dti = c->dti; s.cls = c->cls;
+    s.ceh = c->ceh; s.ceu = c->ceu; s.cev = c->cev; s.cgx = c->cgx; s.cgy = c->cgy; s.cew = c->cew;
+    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.cls = c->cls; s.pw_list = c->pw_list;
     s.scal = c->scal; s.flags = c->flags;
     return s;
 }
@@ -121,12 +148,14 @@ static void morton_order(const std::vector<double> &x, const std::vector<double>
 static void destroy_ctx(swe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    void *ptrs[] = {c->tt, c->te, c->tp, c->slotL, c->slotR, c->cgeo, c->node, c->en, c->area, c->elen, c->dmin,
-                    c->cfl_mask, c->cell_old, c->edge_old, c->node_old, c->bufA[0], c->bufA[1], c->bufA[2],
-                    c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->csx, c->csy, c->cew, c->f0, c->f1,
-                    c->f2, c->maxw, c->dti, c->cls, c->scal, c->flags, c->diag, c->stage_aos, c->send_cells,
-                    c->recv_cells};
+    void *ptrs[] = {c->tt, c->te, c->tp, c->slotL, c->slotR, c->cgeo, c->node, c->en, c->area, c->cb, c->elen, c->dmin,
+                    c->n2c_start, c->n2c_cells, c->cfl_mask, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
+                    c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
+                    c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->scal, c->flags, c->diag, c->stage_aos,
+                    c->send_cells, c->recv_cells};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &p : c->kt_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto &p : c->kt_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete c;
 }
 
@@ -141,7 +170,7 @@ static int ensure_stage(swe_ctx *c, size_t n_doubles) {
 
 template <int FLUX>
 static void launch_flux_ws(swe_ctx *c, const DevMesh &m, const DevFields &s, int ws) {
-    const int g = nblk(c->ne, kBlock);
+    const int g = std::min(nblk(c->ne, kBlock), c->sms * SWE_K2_GRID_PER_SM);
     const double ac = std::fabs(c->cor);
     switch (ws) {
         case SWE_RUSANOV: k_flux<FLUX, WS_RUSANOV><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
@@ -198,10 +227,12 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
                                       "); this library has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(SWE_ERR_INVALID, "swe_create: bad device ordinal");
     if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(SWE_ERR_CUDA, cudaGetErrorString(ce));
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
 
     swe_ctx *c = new (std::nothrow) swe_ctx();
     if (!c) return fail(SWE_ERR_NOMEM, "out of host memory");
-    c->device = device; c->nt = (int)nt; c->ne = (int)ne; c->nn = (int)nn;
+    c->device = device; c->nt = (int)nt; c->ne = (int)ne; c->nn = (int)nn; c->sms = sm_count;
     c->cor = mesh->cor; c->tau = mesh->tau;
     c->reordered = reorder != 0;
 
@@ -273,6 +304,16 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
         CREATE_TRY(cudaMemcpy(c->tp, h_tp.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(c->tt, h_tt.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(c->te, h_te.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
+        // node -> incident cells (CSR, device numbering): pass 2 gathers the node maxima over it
+        std::vector<int> start((size_t)nn + 1, 0);
+        for (int64_t k = 0; k < 3 * nt; ++k) start[(size_t)h_tp[k] + 1]++;
+        for (int64_t p = 0; p < nn; ++p) start[p + 1] += start[p];
+        std::vector<int> fill(start.begin(), start.end() - 1), cells((size_t)3 * nt);
+        for (int64_t d = 0; d < nt; ++d)
+            for (int k = 0; k < 3; ++k) cells[fill[h_tp[(size_t)k * nt + d]]++] = (int)d;
+        CREATE_TRY(dalloc(&c->n2c_start, (size_t)nn + 1)); CREATE_TRY(dalloc(&c->n2c_cells, (size_t)3 * nt));
+        CREATE_TRY(cudaMemcpy(c->n2c_start, start.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(c->n2c_cells, cells.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
     }
     int *d_ep0 = nullptr, *d_ep1 = nullptr, *d_et0 = nullptr, *d_et1 = nullptr;
     {
@@ -311,12 +352,12 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
         CREATE_TRY(cudaMemcpy(c->node_old, inv.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
     }
     // ---- geometry on device ----
-    CREATE_TRY(dalloc(&c->cgeo, (size_t)nt)); CREATE_TRY(dalloc(&c->area, (size_t)nt));
+    CREATE_TRY(dalloc(&c->cgeo, (size_t)nt)); CREATE_TRY(dalloc(&c->area, (size_t)nt)); CREATE_TRY(dalloc(&c->cb, (size_t)nt));
     CREATE_TRY(dalloc(&c->slotL, (size_t)ne)); CREATE_TRY(dalloc(&c->slotR, (size_t)ne));
     CREATE_TRY(dalloc(&c->en, (size_t)ne)); CREATE_TRY(dalloc(&c->elen, (size_t)ne)); CREATE_TRY(dalloc(&c->dmin, (size_t)ne));
     CREATE_TRY(cudaMemset(c->slotR, 0xff, sizeof(int) * ne));
     CREATE_TRY(cudaMemset(c->slotL, 0xff, sizeof(int) * ne));
-    k_setup_cells<<<nblk(nt, 256), 256>>>(c->nt, c->tp, c->tt, c->node, c->cgeo, c->area);
+    k_setup_cells<<<nblk(nt, 256), 256>>>(c->nt, c->tp, c->tt, c->node, c->cgeo, c->area, c->cb);
     k_setup_slots<<<nblk(nt, 256), 256>>>(c->nt, c->te, c->slotL, c->slotR);
     k_setup_edges<<<nblk(ne, 256), 256>>>(c->ne, c->nt, d_ep0, d_ep1, d_et0, d_et1, c->node, c->cgeo, c->area, c->en,
                                          c->elen, c->dmin);
@@ -328,9 +369,9 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
     for (int q = 0; q < 3; ++q) { CREATE_TRY(dalloc(&c->bufA[q], (size_t)nt)); CREATE_TRY(dalloc(&c->bufB[q], (size_t)nt)); }
     c->cur = c->bufA; c->sav = c->bufA;
     CREATE_TRY(dalloc(&c->ceh, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->ceu, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->cev, (size_t)3 * nt));
-    CREATE_TRY(dalloc(&c->csx, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->csy, (size_t)3 * nt));
+    CREATE_TRY(dalloc(&c->cgx, (size_t)nt)); CREATE_TRY(dalloc(&c->cgy, (size_t)nt)); CREATE_TRY(dalloc(&c->pw_list, (size_t)nt));
     CREATE_TRY(dalloc(&c->f0, (size_t)ne)); CREATE_TRY(dalloc(&c->f1, (size_t)ne)); CREATE_TRY(dalloc(&c->f2, (size_t)ne));
-    CREATE_TRY(dalloc(&c->maxw, (size_t)nn)); CREATE_TRY(dalloc(&c->dti, (size_t)nt)); CREATE_TRY(dalloc(&c->cls, (size_t)nt));
+    CREATE_TRY(dalloc(&c->dti, (size_t)nt)); CREATE_TRY(dalloc(&c->cls, (size_t)nt));
     CREATE_TRY(dalloc(&c->scal, 8)); CREATE_TRY(dalloc(&c->flags, 4));
     CREATE_TRY(dalloc(&c->diag, (size_t)6 * kDiagBlocks + 8));
     for (int q = 0; q < 3; ++q) {
@@ -338,13 +379,13 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
         CREATE_TRY(cudaMemset(c->bufB[q], 0, sizeof(double) * nt));
     }
     CREATE_TRY(cudaMemset(c->ceh, 0, sizeof(double) * 3 * nt)); CREATE_TRY(cudaMemset(c->ceu, 0, sizeof(double) * 3 * nt));
-    CREATE_TRY(cudaMemset(c->cev, 0, sizeof(double) * 3 * nt)); CREATE_TRY(cudaMemset(c->csx, 0, sizeof(double) * 3 * nt));
-    CREATE_TRY(cudaMemset(c->csy, 0, sizeof(double) * 3 * nt));
+    CREATE_TRY(cudaMemset(c->cev, 0, sizeof(double) * 3 * nt)); CREATE_TRY(cudaMemset(c->cgx, 0, sizeof(double) * nt));
+    CREATE_TRY(cudaMemset(c->cgy, 0, sizeof(double) * nt));
     CREATE_TRY(cudaMemset(c->f0, 0, sizeof(double) * ne)); CREATE_TRY(cudaMemset(c->f1, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->f2, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->dti, 0, sizeof(double) * nt)); CREATE_TRY(cudaMemset(c->cls, 0, nt));
     CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 4));
-    const double scal0[8] = {1.0, 0.0, 0.0, 0, 0, 0, 0, 0};
+    const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 0, 0, 0, 0};
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
@@ -423,13 +464,18 @@ SWE_API int swe_compute_interface_values(swe_ctx *c) {
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     int rc;
-    k_stage_begin<<<nblk(std::max(c->nn, 1), 256), 256, 0, c->stream>>>(m, s);
-    if ((rc = launch_check(c, "k_stage_begin"))) return rc;
-    if (c->taps) k_reconstruct<true><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
-    else k_reconstruct<false><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
+    CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, 2 * sizeof(int), c->stream));  // part-wet list + K1 tile counters
+    int kt = kt_begin(c, KT_RECONSTRUCT);
+    // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
+    const int g1 = (SWE_K1_MODE == 0) ? nblk(c->nt, kBlock) : std::min(nblk(c->nt, kBlock), c->sms * SWE_K1_GRID_PER_SM);
+    if (c->taps) k_reconstruct<true><<<g1, kBlock, 0, c->stream>>>(m, s);
+    else k_reconstruct<false><<<g1, kBlock, 0, c->stream>>>(m, s);
+    kt_end(c, kt);
     if ((rc = launch_check(c, "k_reconstruct"))) return rc;
-    if (c->taps) k_partwet2<true><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
-    else k_partwet2<false><<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s, c->cor);
+    kt = kt_begin(c, KT_PARTWET2);
+    if (c->taps) k_partwet2<true><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
+    else k_partwet2<false><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
+    kt_end(c, kt);
     return launch_check(c, "k_partwet2");
 }
 
@@ -442,7 +488,9 @@ SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
+    const int kt = kt_begin(c, KT_FLUX);
     if (flux == SWE_HLL) launch_flux_ws<FLUX_HLL>(c, m, s, ws); else launch_flux_ws<FLUX_HLLC>(c, m, s, ws);
+    kt_end(c, kt);
     return launch_check(c, "k_flux");
 }
 
@@ -458,7 +506,9 @@ static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     int rc;
+    int kt = kt_begin(c, KT_DRAIN);
     k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+    kt_end(c, kt);
     if ((rc = launch_check(c, "k_drain"))) return rc;
     double **outb = c->cur;
     if (c->saved_pending && c->sav == c->cur) {  // first stage after save: keep U0 intact
@@ -466,12 +516,17 @@ static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double
         c->saved_pending = false;
     }
     const int g = nblk(c->nt, kBlock);
-    if (a0 == 0.)
-        k_update<true><<<g, kBlock, 0, c->stream>>>(m, s, nullptr, nullptr, nullptr, outb[0], outb[1], outb[2], a0, a1,
-                                                    dt_host, dt_coef);
-    else
-        k_update<false><<<g, kBlock, 0, c->stream>>>(m, s, c->sav[0], c->sav[1], c->sav[2], outb[0], outb[1], outb[2],
-                                                     a0, a1, dt_host, dt_coef);
+    kt = kt_begin(c, KT_UPDATE);
+    const bool cor_on = c->cor != 0.;
+#define SWE_UPD(PLAIN, COR, W0, U0, V0) \
+    k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor)
+    if (a0 == 0.) {
+        if (cor_on) SWE_UPD(true, true, nullptr, nullptr, nullptr); else SWE_UPD(true, false, nullptr, nullptr, nullptr);
+    } else {
+        if (cor_on) SWE_UPD(false, true, c->sav[0], c->sav[1], c->sav[2]); else SWE_UPD(false, false, c->sav[0], c->sav[1], c->sav[2]);
+    }
+#undef SWE_UPD
+    kt_end(c, kt);
     if ((rc = launch_check(c, "k_update"))) return rc;
     c->cur = outb;
     return SWE_OK;
@@ -587,7 +642,7 @@ static int edge_tap(swe_ctx *c, double *out, int which) {
     int rc = ensure_stage(c, std::max(n, (size_t)3 * c->nt));
     if (rc) return rc;
     CUDA_TRY(c, cudaMemsetAsync(c->stage_aos, 0, sizeof(double) * n, c->stream));
-    k_edge_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(dev_mesh(c), dev_fields(c), c->cell_old, c->edge_old, which, c->stage_aos);
+    k_edge_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(dev_mesh(c), dev_fields(c), c->cell_old, c->edge_old, which, c->cor, c->stage_aos);
     if ((rc = launch_check(c, "k_edge_out"))) return rc;
     return tap_out(c, out, n);
 }
@@ -612,7 +667,15 @@ static int scalar_tap(swe_ctx *c, double *out, const double *src, int n, const i
     if ((rc = launch_check(c, "k_scalar_out"))) return rc;
     return tap_out(c, out, (size_t)n);
 }
-SWE_API int swe_get_node_max_w(swe_ctx *c, double *out) { return c ? scalar_tap(c, out, c->maxw, c->nn, c->node_old) : SWE_ERR_INVALID; }
+SWE_API int swe_get_node_max_w(swe_ctx *c, double *out) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)3 * c->nt);
+    if (rc) return rc;
+    k_node_maxw_out<<<nblk(c->nn, 256), 256, 0, c->stream>>>(dev_mesh(c), dev_fields(c), c->node_old, c->stage_aos);
+    if ((rc = launch_check(c, "k_node_maxw_out"))) return rc;
+    return tap_out(c, out, (size_t)c->nn);
+}
 SWE_API int swe_get_draining_dt(swe_ctx *c, double *out) { return c ? scalar_tap(c, out, c->dti, c->nt, c->cell_old) : SWE_ERR_INVALID; }
 SWE_API int swe_get_cell_class(swe_ctx *c, int8_t *out) {
     if (!c || !out) return SWE_ERR_INVALID;
@@ -637,6 +700,29 @@ SWE_API int swe_diagnostics(swe_ctx *c, double out[6]) {
     CUDA_TRY(c, cudaMemcpyAsync(out, c->diag + 6 * kDiagBlocks, sizeof(double) * 6, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return SWE_OK;
+}
+
+// ---- per-kernel timing (CUDA events on the ctx stream) ----
+SWE_API int swe_kernel_timing(swe_ctx *c, int enable) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto &p : c->kt_pairs) c->kt_pool.push_back({p.a, p.b});
+    c->kt_pairs.clear();
+    c->ktiming = enable != 0;
+    return SWE_OK;
+}
+SWE_API int swe_kernel_times(swe_ctx *c, int32_t max_kinds, double *ms_total, int64_t *counts, const char **names) {
+    if (!c || !ms_total || !counts || max_kinds < KT_COUNT) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < KT_COUNT; ++k) { ms_total[k] = 0.; counts[k] = 0; if (names) names[k] = kt_names[k]; }
+    for (auto &p : c->kt_pairs) {
+        float ms = 0.f;
+        CUDA_TRY(c, cudaEventElapsedTime(&ms, p.a, p.b));
+        ms_total[p.id] += ms; counts[p.id]++;
+    }
+    return KT_COUNT;
 }
 
 // ---- multi-GPU support ----

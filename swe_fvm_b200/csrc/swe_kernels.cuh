@@ -8,6 +8,8 @@
 //   edges : slotL/slotR[e] (where the two cells keep their side of edge e), en[e] = (nx, ny)
 //           outward normal of EdgeTriangs[0], elen[e], dmin[e] = min(2A_l/L, 2A_r/L)
 //   state : w/u/v[i] SoA, ping-pong buffers (no U0 copy kernels)
+//   node maxima of the reconstructed surface (m_max_wp upstream) are NOT stored: the part-wet
+//   pass gathers them over the node's incident cells (deterministic, no atomics on doubles)
 //   edge-side values (m_edg, m_src upstream) are stored CELL-major, c*[k*nt+i] = value of cell
 //   i's side of its k-th edge: written coalesced by the reconstruction, read coalesced by the
 //   stage update, gathered once by the flux kernel through slotL/slotR.
@@ -23,8 +25,9 @@ struct DevMesh {
     int nt, ne, nn;
     const int *tt, *te, *tp;
     const double4 *cgeo;
-    const double *area;
+    const double *area, *cb;
     const double4 *node;
+    const int *n2c_start, *n2c_cells;  // node -> incident cells (CSR), pass 2 and taps only
     const int *slotL, *slotR;
     const double2 *en;
     const double *elen, *dmin;
@@ -34,26 +37,19 @@ struct DevMesh {
 struct DevFields {
     double *w, *u, *v;               // current state (stage input)
     double *ceh, *ceu, *cev;         // [3*nt] edge-side depth h_e and (damped) velocities
-    double *csx, *csy;               // [3*nt] edge-side source (grad w + cor * (-v, u))
+    double *cgx, *cgy;               // [nt] w-gradient of the cell's reconstruction (row 0 of m_grad);
+                                     // m_src = (cgx, cgy) + cor * (-v_e, u_e) is formed in the update
     double *cew;                     // [3*nt] edge-side w, taps only (nullable)
     double *f0, *f1, *f2;            // [ne] fluxes
-    double *maxw;                    // [nn] node maxima of reconstructed w (pass 1)
     double *dti;                     // [nt] draining dt
     signed char *cls;                // [nt] 0 dry, 1 part-wet, 2 full-wet
-    double *scal;                    // [0] min_len_to_wavespeed, [1] dt, [2] time
-    int *flags;                      // [0] non-finite state seen
+    int *pw_list;                    // [nt] compacted ids of part-wet cells (pass 2 work list)
+    double *scal;                    // [0] min_len_to_wavespeed, [1] dt, [2] time, [3] running min
+    int *flags;                      // [0] non-finite state seen, [1] part-wet count, [2] K1 tile counter,
+                                     // [3] flux block ticket
 };
 
 constexpr int kBlock = 128;
-
-// ---------------------------------------------------------------------------------------
-// stage begin: m_max_wp = node bathymetry (src/SpaceDisc.cpp:34); min_len = 1 (:56)
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_stage_begin(DevMesh m, DevFields s) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) s.scal[0] = 1.0;
-    if (p < m.nn) s.maxw[p] = m.node[p].z;
-}
 
 // MUSCL::AtPoint (include/MUSCLObject.h:26-33) for one component set
 struct Muscl {
@@ -65,7 +61,7 @@ struct Muscl {
 // local edge k whose midpoint is (mx, my, mb); writes the cell-major slots.
 template <bool TAPS>
 __device__ __forceinline__ void emit_edge(const DevFields &s, int slot, const Muscl &M, double cx, double cy,
-                                          double mx, double my, double mb, double cor) {
+                                          double mx, double my, double mb) {
     const double dx = mx - cx, dy = my - cy;
     double a0 = M.o0 + (M.g00 * dx + M.g01 * dy);
     double a1 = M.o1 + (M.g10 * dx + M.g11 * dy);
@@ -84,10 +80,10 @@ __device__ __forceinline__ void emit_edge(const DevFields &s, int slot, const Mu
     }
     s.ceh[slot] = eh; s.ceu[slot] = eu; s.cev[slot] = ev;
     if (TAPS) s.cew[slot] = ew;
-    // MUSCL::Gradient(p) (include/MUSCLObject.h:41-48) always evaluates to m_grad: when the
-    // reconstructed depth is negative AtPoint returns the dry state, whose depth is exactly 0.
-    s.csx[slot] = M.g00 + cor * (-ev);
-    s.csy[slot] = M.g01 + cor * eu;
+    // m_src (src/SpaceDisc.cpp:26-29) = Gradient(edge).row(0) + cor * (-v_e, u_e). MUSCL::Gradient(p)
+    // (include/MUSCLObject.h:41-48) always evaluates to m_grad: when the reconstructed depth is
+    // negative AtPoint returns the dry state, whose depth is exactly 0. So only the cell's
+    // (g00, g01) is stored (once per cell) and the sum is formed where it is consumed.
 }
 
 __device__ __forceinline__ double muscl_w_at(const Muscl &M, double cx, double cy, double px, double py, double pz) {
@@ -98,24 +94,53 @@ __device__ __forceinline__ double muscl_w_at(const Muscl &M, double cx, double c
 
 // ---------------------------------------------------------------------------------------
 // K1: classification + pass-1 reconstruction of every cell (src/SpaceDisc.cpp:37-45,
-// src/MUSCLObject.cpp:13-112), node maxima by order-independent integer atomics.
+// src/MUSCLObject.cpp:13-112). Part-wet cells are appended to the pass-2 work list.
 // ---------------------------------------------------------------------------------------
+// K1 dispatch (SWE_K1_MODE): 0 = one block per 128-cell tile, hardware in-order dispatch keeps
+// the active window of the mesh compact (best L1/L2 reuse of the shared nodes / neighbours);
+// 1 = persistent grid-stride with next-cell id prefetch; 2 = persistent warps pulling 128-cell
+// tiles in order from an atomic counter (compact window + id prefetch).
+// A cp.async (LDGSTS) double-buffered variant that staged all 36 inputs of a cell in shared
+// memory was measured slower (5.1 ms vs 3.5 ms at 64M cells: profiles/r1_k1_cpasync_*): the
+// 221 KB of smem leaves no L1 and persistent blocks drift apart, doubling DRAM reads.
+#ifndef SWE_K1_MODE
+#define SWE_K1_MODE 1
+#endif
+#ifndef SWE_K1_MIN_BLOCKS
+#define SWE_K1_MIN_BLOCKS 3
+#endif
+#ifndef SWE_K1_GRID_PER_SM
+#define SWE_K1_GRID_PER_SM 3
+#endif
+__device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32-byte read-only gather
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
 template <bool TAPS>
-__global__ void __launch_bounds__(kBlock) k_reconstruct(DevMesh m, DevFields s, double cor) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFields &s, const int i, const int ip0,
+                                                 const int ip1, const int ip2, const int it0, const int it1,
+                                                 const int it2) {
     const int nt = m.nt;
-    if (i >= nt) return;
-    const int ip0 = m.tp[i], ip1 = m.tp[nt + i], ip2 = m.tp[2 * nt + i];
-    const int it0 = m.tt[i], it1 = m.tt[nt + i], it2 = m.tt[2 * nt + i];
-    const double4 P0 = m.node[ip0], P1 = m.node[ip1], P2 = m.node[ip2];
-    const double4 Gi = m.cgeo[i];
+    // all gathers are issued up front (two dependent round trips in total: ids -> data); the
+    // neighbour ids of boundary triangles are clamped, their values are never used
+    const int jt[3] = {max(it0, 0), max(it1, 0), max(it2, 0)};
+    const double4 P0 = ldg4(m.node + ip0), P1 = ldg4(m.node + ip1), P2 = ldg4(m.node + ip2);
+    const double4 Gi = ldg4(m.cgeo + i);
+    const double w = __ldg(s.w + i), u = __ldg(s.u + i), v = __ldg(s.v + i);
+    double N[3][3];
+    double4 Gn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        N[k][0] = __ldg(s.w + jt[k]); N[k][1] = __ldg(s.u + jt[k]); N[k][2] = __ldg(s.v + jt[k]);
+        Gn[k] = ldg4(m.cgeo + jt[k]);
+    }
     const double cx = Gi.x, cy = Gi.y, cb = Gi.z;
-    const double w = s.w[i], u = s.u[i], v = s.v[i];
 
     // edge midpoints E(ie[k]) = 0.5 (P(ep0) + P(ep1)), edge k joins ip[k], ip[k+1] (S1)
-    const double mx0 = 0.5 * (P0.x + P1.x), my0 = 0.5 * (P0.y + P1.y), mb0 = 0.5 * (P0.z + P1.z);
-    const double mx1 = 0.5 * (P1.x + P2.x), my1 = 0.5 * (P1.y + P2.y), mb1 = 0.5 * (P1.z + P2.z);
-    const double mx2 = 0.5 * (P2.x + P0.x), my2 = 0.5 * (P2.y + P0.y), mb2 = 0.5 * (P2.z + P0.z);
+    const double mxk[3] = {0.5 * (P0.x + P1.x), 0.5 * (P1.x + P2.x), 0.5 * (P2.x + P0.x)};
+    const double myk[3] = {0.5 * (P0.y + P1.y), 0.5 * (P1.y + P2.y), 0.5 * (P2.y + P0.y)};
+    const double mbk[3] = {0.5 * (P0.z + P1.z), 0.5 * (P1.z + P2.z), 0.5 * (P2.z + P0.z)};
 
     const bool bnd = (it0 | it1 | it2) < 0;
     const double bmax = smax(smax(P0.z, P1.z), P2.z);
@@ -131,25 +156,23 @@ __global__ void __launch_bounds__(kBlock) k_reconstruct(DevMesh m, DevFields s, 
     } else if (!full) {  // ReconstructPartWetCell1 (:86-112)
         const double bmin = smin(smin(P0.z, P1.z), P2.z);
         M.o0 = partwet1_level(w, cb, bmax, bmin); M.o1 = u; M.o2 = v;
+        s.pw_list[atomicAdd(&s.flags[1], 1)] = i;
     } else {  // ReconstructFullWetCell (:38-84), S2: plane gradients of w, u, v
         M.o0 = w; M.o1 = u; M.o2 = v;
-        double X[3][2], V[3][3], N[3][3];
+        double X[3][2], V[3][3];
         bool zero_grad = false;
-        const int itk[3] = {it0, it1, it2};
-        const double mxk[3] = {mx0, mx1, mx2}, myk[3] = {my0, my1, my2}, mbk[3] = {mb0, mb1, mb2};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const int j = itk[k];
-            const double wj = s.w[j], uj = s.u[j], vj = s.v[j];
-            const double4 Gj = m.cgeo[j];
-            N[k][0] = wj; N[k][1] = uj; N[k][2] = vj;
+            const int j = jt[k];
+            const double wj = N[k][0], uj = N[k][1], vj = N[k][2];
+            const double4 Gj = Gn[k];
             if (Gj.w < wj) {  // IsFullWetCell(j): bfull = +inf on boundary triangles
                 X[k][0] = Gj.x; X[k][1] = Gj.y;
                 V[k][0] = wj; V[k][1] = uj; V[k][2] = vj;
             } else if (!is_wet(wj - Gj.z)) {  // IsDryCell(j) -> zero gradient
                 zero_grad = true;
                 X[k][0] = X[k][1] = 0.; V[k][0] = V[k][1] = V[k][2] = 0.;
-            } else {  // part-wet neighbour: its PartWet1 value at the shared edge midpoint
+            } else {  // part-wet neighbour (rare): its PartWet1 value at the shared edge midpoint
                 const double z0 = m.node[m.tp[j]].z, z1 = m.node[m.tp[nt + j]].z, z2 = m.node[m.tp[2 * nt + j]].z;
                 const double b13 = smax(smax(z0, z1), z2), b23 = smin(smin(z0, z1), z2);
                 double a0 = partwet1_level(wj, Gj.z, b13, b23), a1 = uj, a2 = vj;
@@ -162,10 +185,9 @@ __global__ void __launch_bounds__(kBlock) k_reconstruct(DevMesh m, DevFields s, 
             }
         }
         if (!zero_grad) {
-            double df[3][2];
             const Lu2 lu = lu2_factor(X[0][0], X[0][1], X[1][0], X[1][1], X[2][0], X[2][1]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) lu2_solve(lu, V[0][c], V[1][c], V[2][c], df[c][0], df[c][1]);
+            double df[3][2];
+            lu2_solve(lu, V[0][0], V[1][0], V[2][0], df[0][0], df[0][1]);
             // vertex positivity (:66-72): dx = P(ip) * (I - 1/3), evaluated literally
             const double md = 1. - 1. / 3., mo = 0. - 1. / 3.;
             const double dx0 = (P0.x * md + P1.x * mo) + P2.x * mo, dy0 = (P0.y * md + P1.y * mo) + P2.y * mo;
@@ -174,11 +196,14 @@ __global__ void __launch_bounds__(kBlock) k_reconstruct(DevMesh m, DevFields s, 
             const double hp0 = ((df[0][0] * dx0 + df[0][1] * dy0) + w) - P0.z;
             const double hp1 = ((df[0][0] * dx1 + df[0][1] * dy1) + w) - P1.z;
             const double hp2 = ((df[0][0] * dx2 + df[0][1] * dy2) + w) - P2.z;
-            if (!(is_wet(hp0) && is_wet(hp1) && is_wet(hp2))) {
+            const bool positive = is_wet(hp0) && is_wet(hp1) && is_wet(hp2);
+            lu2_solve(lu, V[0][1], V[1][1], V[2][1], df[1][0], df[1][1]);
+            lu2_solve(lu, V[0][2], V[1][2], V[2][2], df[2][0], df[2][1]);
+            if (!positive) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) df[c][0] = df[c][1] = 0.;
             }
-            // on/off TVD limiter (:74-81)
+            // on/off TVD limiter (:74-81) against the neighbours' cell means
             double tvd[3] = {1., 1., 1.};
             const double own[3] = {w, u, v};
 #pragma unroll
@@ -196,86 +221,177 @@ __global__ void __launch_bounds__(kBlock) k_reconstruct(DevMesh m, DevFields s, 
             M.g20 = tvd[2] * df[2][0]; M.g21 = tvd[2] * df[2][1];
         }
     }
-    // UpdateInterfaceValues (src/SpaceDisc.cpp:15-31)
-    atomic_max_double(&s.maxw[ip0], muscl_w_at(M, cx, cy, P0.x, P0.y, P0.z));
-    atomic_max_double(&s.maxw[ip1], muscl_w_at(M, cx, cy, P1.x, P1.y, P1.z));
-    atomic_max_double(&s.maxw[ip2], muscl_w_at(M, cx, cy, P2.x, P2.y, P2.z));
-    emit_edge<TAPS>(s, i, M, cx, cy, mx0, my0, mb0, cor);
-    emit_edge<TAPS>(s, nt + i, M, cx, cy, mx1, my1, mb1, cor);
-    emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mx2, my2, mb2, cor);
+    // UpdateInterfaceValues (src/SpaceDisc.cpp:15-31); the node maxima (:23) are gathered in pass 2
+    s.cgx[i] = M.g00; s.cgy[i] = M.g01;
+    emit_edge<TAPS>(s, i, M, cx, cy, mxk[0], myk[0], mbk[0]);
+    emit_edge<TAPS>(s, nt + i, M, cx, cy, mxk[1], myk[1], mbk[1]);
+    emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mxk[2], myk[2], mbk[2]);
+}
+
+template <bool TAPS>
+__global__ void __launch_bounds__(kBlock, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s) {
+    const int nt = m.nt;
+#if SWE_K1_MODE == 0
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    reconstruct_cell<TAPS>(m, s, i, __ldg(m.tp + i), __ldg(m.tp + nt + i), __ldg(m.tp + 2 * nt + i), __ldg(m.tt + i),
+                           __ldg(m.tt + nt + i), __ldg(m.tt + 2 * nt + i));
+#elif SWE_K1_MODE == 1
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    int ip0 = __ldg(m.tp + i), ip1 = __ldg(m.tp + nt + i), ip2 = __ldg(m.tp + 2 * nt + i);
+    int it0 = __ldg(m.tt + i), it1 = __ldg(m.tt + nt + i), it2 = __ldg(m.tt + 2 * nt + i);
+    for (;;) {
+        const int nx = i + stride;
+        int np0 = 0, np1 = 0, np2 = 0, nt0 = 0, nt1 = 0, nt2 = 0;
+        if (nx < nt) {
+            np0 = __ldg(m.tp + nx); np1 = __ldg(m.tp + nt + nx); np2 = __ldg(m.tp + 2 * nt + nx);
+            nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
+        }
+        reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
+        if (nx >= nt) break;
+        i = nx; ip0 = np0; ip1 = np1; ip2 = np2; it0 = nt0; it1 = nt1; it2 = nt2;
+    }
+#else
+    // every warp pulls 128-cell tiles in order from flags[2] (reset before the launch)
+    const int lane = threadIdx.x & 31;
+    const int ntiles = (nt + 127) >> 7;
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(&s.flags[2], 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&s.flags[2], 1);  // in flight while this tile is processed
+        const int base = (tile << 7) + lane;
+        int i = base;
+        int ip0 = 0, ip1 = 0, ip2 = 0, it0 = 0, it1 = 0, it2 = 0;
+        if (i < nt) {
+            ip0 = __ldg(m.tp + i); ip1 = __ldg(m.tp + nt + i); ip2 = __ldg(m.tp + 2 * nt + i);
+            it0 = __ldg(m.tt + i); it1 = __ldg(m.tt + nt + i); it2 = __ldg(m.tt + 2 * nt + i);
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+            const int nx = base + 32 * (sub + 1);
+            int np0 = 0, np1 = 0, np2 = 0, nt0 = 0, nt1 = 0, nt2 = 0;
+            if (sub < 3 && nx < nt) {
+                np0 = __ldg(m.tp + nx); np1 = __ldg(m.tp + nt + nx); np2 = __ldg(m.tp + 2 * nt + nx);
+                nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
+            }
+            if (i < nt) reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
+            i = nx; ip0 = np0; ip1 = np1; ip2 = np2; it0 = nt0; it1 = nt1; it2 = nt2;
+        }
+        tile = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+#endif
+}
+
+// Value at node Q = (qx, qy, qz) of cell t's PASS-1 reconstruction, i.e. one term of the max in
+// m_max_wp[node] = max(m_max_wp[node], muscl.AtPoint(P(node))[0]) (src/SpaceDisc.cpp:23).
+__device__ __noinline__ double pass1_w_at_node(const DevMesh &m, const DevFields &s, int t, double qx, double qy, double qz) {
+    const int nt = m.nt;
+    const double4 G = m.cgeo[t];
+    const int c = s.cls[t];
+    double o0, g0, g1;
+    if (c == 1) {  // PartWet1: flat level, zero gradient (its cgx/cgy may already hold pass-2 values)
+        const double z0 = m.node[m.tp[t]].z, z1 = m.node[m.tp[nt + t]].z, z2 = m.node[m.tp[2 * nt + t]].z;
+        o0 = partwet1_level(s.w[t], G.z, smax(smax(z0, z1), z2), smin(smin(z0, z1), z2));
+        g0 = 0.; g1 = 0.;
+    } else {
+        o0 = (c == 0) ? G.z : s.w[t];
+        g0 = s.cgx[t]; g1 = s.cgy[t];
+    }
+    double a0 = o0 + (g0 * (qx - G.x) + g1 * (qy - G.y));
+    if (!((a0 - qz) >= 0)) a0 = qz;
+    return a0;
+}
+__device__ __forceinline__ double node_max_w(const DevMesh &m, const DevFields &s, int p, double qx, double qy, double qz) {
+    double mx = qz;  // m_max_wp starts from the node bathymetry (src/SpaceDisc.cpp:34)
+    for (int q = m.n2c_start[p]; q < m.n2c_start[p + 1]; ++q) mx = smax(mx, pass1_w_at_node(m, s, m.n2c_cells[q], qx, qy, qz));
+    return mx;
 }
 
 // ---------------------------------------------------------------------------------------
-// K1b: pass 2, ReconstructPartWetCell2 (src/MUSCLObject.cpp:114-191, S3) for part-wet cells;
-// reads the node maxima of pass 1 only and does not update them (S8).
+// K1b: pass 2, ReconstructPartWetCell2 (src/MUSCLObject.cpp:114-191, S3) over the compacted list
+// of part-wet cells. The node maximum it needs is gathered from the PASS-1 reconstructions of
+// the cells around the lowest vertex (S8: pass 2 never sees pass-2 values) — a deterministic
+// gather instead of the reference's scatter-max, no atomics on doubles.
 // ---------------------------------------------------------------------------------------
+constexpr int kPw2Blocks = 296;
 template <bool TAPS>
-__global__ void __launch_bounds__(kBlock) k_partwet2(DevMesh m, DevFields s, double cor) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kBlock) k_partwet2(DevMesh m, DevFields s) {
     const int nt = m.nt;
-    if (i >= nt) return;
-    if (s.cls[i] != 1) return;
-    const int ip0 = m.tp[i], ip1 = m.tp[nt + i], ip2 = m.tp[2 * nt + i];
-    const double4 P0 = m.node[ip0], P1 = m.node[ip1], P2 = m.node[ip2];
-    const double4 Gi = m.cgeo[i];
-    const double cx = Gi.x, cy = Gi.y, cb = Gi.z;
-    const double w = s.w[i], u = s.u[i], v = s.v[i];
-    // three conditional swaps (:119-121)
-    double4 Q0 = P0, Q1 = P1, Q2 = P2;
-    int q0 = ip0, q1 = ip1, q2 = ip2;
-    if (Q0.z > Q1.z) { double4 t = Q0; Q0 = Q1; Q1 = t; int ti = q0; q0 = q1; q1 = ti; }
-    if (Q1.z > Q2.z) { double4 t = Q1; Q1 = Q2; Q2 = t; int ti = q1; q1 = q2; q2 = ti; }
-    if (Q0.z > Q1.z) { double4 t = Q0; Q0 = Q1; Q1 = t; int ti = q0; q0 = q1; q1 = ti; }
-    const double b23 = Q0.z, b12 = Q1.z, b13 = Q2.z;
-    if ((w > b13) || (b13 - b23 < kTol)) return;  // falls back to PartWet1 = what pass 1 wrote
+    const int npw = min(s.flags[1], nt);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npw; q += gridDim.x * blockDim.x) {
+        const int i = s.pw_list[q];
+        const int ip0 = m.tp[i], ip1 = m.tp[nt + i], ip2 = m.tp[2 * nt + i];
+        const double4 P0 = m.node[ip0], P1 = m.node[ip1], P2 = m.node[ip2];
+        const double4 Gi = m.cgeo[i];
+        const double cx = Gi.x, cy = Gi.y, cb = Gi.z;
+        const double w = s.w[i], u = s.u[i], v = s.v[i];
+        // three conditional swaps (:119-121)
+        double4 Q0 = P0, Q1 = P1, Q2 = P2;
+        int q0 = ip0, q1 = ip1, q2 = ip2;
+        if (Q0.z > Q1.z) { double4 t = Q0; Q0 = Q1; Q1 = t; int ti = q0; q0 = q1; q1 = ti; }
+        if (Q1.z > Q2.z) { double4 t = Q1; Q1 = Q2; Q2 = t; int ti = q1; q1 = q2; q2 = ti; }
+        if (Q0.z > Q1.z) { double4 t = Q0; Q0 = Q1; Q1 = t; int ti = q0; q0 = q1; q1 = ti; }
+        const double b23 = Q0.z, b12 = Q1.z, b13 = Q2.z;
+        if ((w > b13) || (b13 - b23 < kTol)) continue;  // falls back to PartWet1 = what pass 1 wrote
 
-    const double w23 = s.maxw[q0];
-    const double h23 = w23 - b23;
-    const double ratio_b = (b12 - b23) / (b13 - b23);
-    const double h_delimiter1 = 1. / 3. * h23 * ratio_b;
-    const double h_delimiter2 = 1. / 3. * h23 * (2. * b13 - b12 - b23) / (b13 - b23);
-    const double hi = w - cb;
-    const double ratio_h = hi / h23;
-    const double S0x = Q0.x, S0y = Q0.y, S0z = w23;
-    double S1x, S1y, S1z, S2x, S2y, S2z;
-    if (hi <= h_delimiter1) {  // one vertex wet
-        const double k2 = sqrt(3. * ratio_h / ratio_b);
-        S1x = k2 * Q1.x + (1. - k2) * Q0.x; S1y = k2 * Q1.y + (1. - k2) * Q0.y; S1z = k2 * Q1.z + (1. - k2) * Q0.z;
-        const double k3 = sqrt(3. * ratio_h * ratio_b);
-        S2x = k3 * Q2.x + (1. - k3) * Q0.x; S2y = k3 * Q2.y + (1. - k3) * Q0.y; S2z = k3 * Q2.z + (1. - k3) * Q0.z;
-    } else if (hi >= h_delimiter2) {  // three vertices wet
-        const double delta_w = 1.5 * (hi - h_delimiter2);
-        S1x = Q1.x; S1y = Q1.y; S1z = Q1.z;
-        S1z += delta_w;
-        S1z += (1. - ratio_b) * h23;
-        S2x = Q2.x; S2y = Q2.y; S2z = Q2.z;
-        S2z += delta_w;
-    } else {  // two vertices wet
-        const double alpha = 3. * ratio_h;
-        const double beta = (b13 - b12) / (b13 - b23);
-        CubicPoly p;
-        p.d = (1. + beta - alpha) / (beta * beta); p.c = (alpha - 3.) / beta; p.b = 0.;
-        const double k1 = 1. - bisection(p, 0., 1.);
-        if (k1 < kTol) return;
-        const double k3 = 1. - beta * (1. - k1);
-        const double bp1 = k1 * b13 + (1. - k1) * b12;
-        S1x = Q1.x; S1y = Q1.y;
-        S1z = b12 + (k1 / k3) * beta * h23;
-        S2x = k1 * Q2.x + (1. - k1) * Q1.x;
-        S2y = k1 * Q2.y + (1. - k1) * Q1.y;
-        S2z = bp1;
+        const double w23 = node_max_w(m, s, q0, Q0.x, Q0.y, Q0.z);
+        const double h23 = w23 - b23;
+        const double ratio_b = (b12 - b23) / (b13 - b23);
+        const double h_delimiter1 = 1. / 3. * h23 * ratio_b;
+        const double h_delimiter2 = 1. / 3. * h23 * (2. * b13 - b12 - b23) / (b13 - b23);
+        const double hi = w - cb;
+        const double ratio_h = hi / h23;
+        const double S0x = Q0.x, S0y = Q0.y, S0z = w23;
+        double S1x, S1y, S1z, S2x, S2y, S2z;
+        if (hi <= h_delimiter1) {  // one vertex wet
+            const double k2 = sqrt(3. * ratio_h / ratio_b);
+            S1x = k2 * Q1.x + (1. - k2) * Q0.x; S1y = k2 * Q1.y + (1. - k2) * Q0.y; S1z = k2 * Q1.z + (1. - k2) * Q0.z;
+            const double k3 = sqrt(3. * ratio_h * ratio_b);
+            S2x = k3 * Q2.x + (1. - k3) * Q0.x; S2y = k3 * Q2.y + (1. - k3) * Q0.y; S2z = k3 * Q2.z + (1. - k3) * Q0.z;
+        } else if (hi >= h_delimiter2) {  // three vertices wet
+            const double delta_w = 1.5 * (hi - h_delimiter2);
+            S1x = Q1.x; S1y = Q1.y; S1z = Q1.z;
+            S1z += delta_w;
+            S1z += (1. - ratio_b) * h23;
+            S2x = Q2.x; S2y = Q2.y; S2z = Q2.z;
+            S2z += delta_w;
+        } else {  // two vertices wet
+            const double alpha = 3. * ratio_h;
+            const double beta = (b13 - b12) / (b13 - b23);
+            CubicPoly p;
+            p.d = (1. + beta - alpha) / (beta * beta); p.c = (alpha - 3.) / beta; p.b = 0.;
+            const double k1 = 1. - bisection(p, 0., 1.);
+            if (k1 < kTol) continue;
+            const double k3 = 1. - beta * (1. - k1);
+            const double bp1 = k1 * b13 + (1. - k1) * b12;
+            S1x = Q1.x; S1y = Q1.y;
+            S1z = b12 + (k1 / k3) * beta * h23;
+            S2x = k1 * Q2.x + (1. - k1) * Q1.x;
+            S2y = k1 * Q2.y + (1. - k1) * Q1.y;
+            S2z = bp1;
+        }
+        Muscl M;
+        M.g10 = M.g11 = M.g20 = M.g21 = 0.;
+        gradient3(S0x, S0y, S0z, S1x, S1y, S1z, S2x, S2y, S2z, M.g00, M.g01);
+        M.o0 = w23 + (M.g00 * (cx - Q0.x) + M.g01 * (cy - Q0.y));
+        M.o1 = u; M.o2 = v;
+        s.cgx[i] = M.g00; s.cgy[i] = M.g01;
+        emit_edge<TAPS>(s, i, M, cx, cy, 0.5 * (P0.x + P1.x), 0.5 * (P0.y + P1.y), 0.5 * (P0.z + P1.z));
+        emit_edge<TAPS>(s, nt + i, M, cx, cy, 0.5 * (P1.x + P2.x), 0.5 * (P1.y + P2.y), 0.5 * (P1.z + P2.z));
+        emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, 0.5 * (P2.x + P0.x), 0.5 * (P2.y + P0.y), 0.5 * (P2.z + P0.z));
     }
-    Muscl M;
-    M.g10 = M.g11 = M.g20 = M.g21 = 0.;
-    gradient3(S0x, S0y, S0z, S1x, S1y, S1z, S2x, S2y, S2z, M.g00, M.g01);
-    M.o0 = w23 + (M.g00 * (cx - Q0.x) + M.g01 * (cy - Q0.y));
-    M.o1 = u; M.o2 = v;
-    const double mx0 = 0.5 * (P0.x + P1.x), my0 = 0.5 * (P0.y + P1.y), mb0 = 0.5 * (P0.z + P1.z);
-    const double mx1 = 0.5 * (P1.x + P2.x), my1 = 0.5 * (P1.y + P2.y), mb1 = 0.5 * (P1.z + P2.z);
-    const double mx2 = 0.5 * (P2.x + P0.x), my2 = 0.5 * (P2.y + P0.y), mb2 = 0.5 * (P2.z + P0.z);
-    emit_edge<TAPS>(s, i, M, cx, cy, mx0, my0, mb0, cor);
-    emit_edge<TAPS>(s, nt + i, M, cx, cy, mx1, my1, mb1, cor);
-    emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mx2, my2, mb2, cor);
+}
+
+// tap: m_max_wp of every node after pass 1 (src/SpaceDisc.cpp:23,34)
+__global__ void k_node_maxw_out(DevMesh m, DevFields s, const int *old, double *dst) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m.nn) return;
+    const double4 Q = m.node[p];
+    dst[old ? old[p] : p] = node_max_w(m, s, p, Q.x, Q.y, Q.z);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -290,25 +406,37 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
+#ifndef SWE_K2_GRID_PER_SM
+#define SWE_K2_GRID_PER_SM 16
+#endif
 template <int FLUX, int WS>
 __global__ void __launch_bounds__(kBlock) k_flux(DevMesh m, DevFields s, double abscor) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ne = m.ne;
+    const int stride = gridDim.x * blockDim.x;
     double l2w = 1.0;  // reset value of m_min_length_to_wavespeed (:56)
-    if (e < m.ne) {
-        const int sl = m.slotL[e], sr = m.slotR[e];
-        const double2 n = m.en[e];
-        double f0, f1, f2;
-        if (sr < 0) {  // SOLID_WALL: ElemFlux(n, {h(lf), 0, 0}) with the cell-mean depth (:67-69)
-            const int lf = sl % m.nt;
-            const double h = s.w[lf] - m.cgeo[lf].z;
-            elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
-        } else {
-            double cand = 1.0;
-            riemann_flux<FLUX, WS>(n.x, n.y, s.ceh[sl], s.ceu[sl], s.cev[sl], s.ceh[sr], s.ceu[sr], s.cev[sr],
-                                   m.dmin[e], abscor, f0, f1, f2, cand);
-            if (m.cfl_mask == nullptr || m.cfl_mask[e]) l2w = cand;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < ne) {
+        int sl = __ldg(m.slotL + e), sr = __ldg(m.slotR + e);
+        for (;;) {
+            const int nx = e + stride;
+            int nsl = 0, nsr = 0;
+            if (nx < ne) { nsl = __ldg(m.slotL + nx); nsr = __ldg(m.slotR + nx); }
+            const double2 n = __ldg(m.en + e);
+            double f0, f1, f2;
+            if (sr < 0) {  // SOLID_WALL: ElemFlux(n, {h(lf), 0, 0}) with the cell-mean depth (:67-69)
+                const int lf = sl % m.nt;
+                const double h = s.w[lf] - m.cb[lf];
+                elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
+            } else {
+                double cand = 1.0;
+                riemann_flux<FLUX, WS>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
+                                       __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand);
+                if (m.cfl_mask == nullptr || m.cfl_mask[e]) l2w = (cand < l2w) ? cand : l2w;
+            }
+            s.f0[e] = f0; s.f1[e] = f1; s.f2[e] = f2;
+            if (nx >= ne) break;
+            e = nx; sl = nsl; sr = nsr;
         }
-        s.f0[e] = f0; s.f1[e] = f1; s.f2[e] = f2;
     }
     __shared__ double red[kBlock / 32];
     l2w = warp_min(l2w);
@@ -317,7 +445,20 @@ __global__ void __launch_bounds__(kBlock) k_flux(DevMesh m, DevFields s, double 
     if (threadIdx.x < 32) {
         double v = (threadIdx.x < kBlock / 32) ? red[threadIdx.x] : 1.0;
         v = warp_min(v);
-        if (threadIdx.x == 0 && v < 1.0) atomic_min_pos_double(&s.scal[0], v);
+        if (threadIdx.x == 0) {
+            // running min in scal[3]; the last block to finish publishes it as
+            // m_min_length_to_wavespeed (scal[0]) and re-arms the accumulator with the reset
+            // value 1.0 (src/SpaceDisc.cpp:56), so no separate reset / finalise kernels exist.
+            if (v < 1.0) atomic_min_pos_double(&s.scal[3], v);
+            __threadfence();
+            const int ticket = atomicAdd(&s.flags[3], 1);
+            if (ticket == (int)gridDim.x - 1) {
+                const double mn = __longlong_as_double(atomicAdd((unsigned long long *)&s.scal[3], 0ull));
+                s.scal[0] = mn;
+                *(volatile double *)&s.scal[3] = 1.0;
+                s.flags[3] = 0;
+            }
+        }
     }
 }
 
@@ -328,7 +469,7 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nt = m.nt;
     if (i >= nt) return;
-    const double h = s.w[i] - m.cgeo[i].z;
+    const double h = s.w[i] - m.cb[i];
     double r;
     if (!is_wet(h)) {
         r = 0.;
@@ -352,19 +493,20 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
 //   else : U = a0*cons(U0) + a1*cons(W) + RHS
 // Reads W (stage input) and writes Wout (may alias W: only the own cell is read).
 // ---------------------------------------------------------------------------------------
-template <bool PLAIN>
+template <bool PLAIN, bool COR>
 __global__ void __launch_bounds__(kBlock) k_update(DevMesh m, DevFields s, const double *__restrict__ w0,
                                                    const double *__restrict__ u0, const double *__restrict__ v0,
                                                    double *wout, double *uout, double *vout, double a0, double a1,
-                                                   double dt_host, double dt_coef) {
+                                                   double dt_host, double dt_coef, double cor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nt = m.nt;
     if (i >= nt) return;
     // dt_coef != 0: stage dt = dt_coef * (device-resident dt), else the host value
     const double dt = (dt_coef != 0.) ? dt_coef * s.scal[1] : dt_host;
-    const double cb = m.cgeo[i].z;
+    const double cb = m.cb[i];
     const double i_area = 1. / m.area[i];
     const double dti = s.dti[i];
+    const double gx = s.cgx[i], gy = s.cgy[i];
     double r0 = 0., r1 = 0., r2 = 0.;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -380,8 +522,12 @@ __global__ void __launch_bounds__(kBlock) k_update(DevMesh m, DevFields s, const
         const double h_ek = s.ceh[k * nt + i];
         const double sc = dtk * sgn * c_ek;
         r0 -= sc * F0; r1 -= sc * F1; r2 -= sc * F2;
-        r1 -= dt * (1. / 3.) * s.csx[k * nt + i] * h_ek;
-        r2 -= dt * (1. / 3.) * s.csy[k * nt + i] * h_ek;
+        // m_src = grad w + cor * (-v_e, u_e) (src/SpaceDisc.cpp:26-29); with cor == 0 the second
+        // term is a signed zero and the sum equals the gradient
+        double sx = gx, sy = gy;
+        if (COR) { sx = gx + cor * (-s.cev[k * nt + i]); sy = gy + cor * s.ceu[k * nt + i]; }
+        r1 -= dt * (1. / 3.) * sx * h_ek;
+        r2 -= dt * (1. / 3.) * sy * h_ek;
         const double2 n = m.en[e];
         const double nx = sgn * n.x, ny = sgn * n.y;  // Norm(e, i) = -Norm(e, other) exactly
         r1 += dtk * (nx * c_ek * (0.5 * h_ek * h_ek));
@@ -423,7 +569,7 @@ __global__ void k_set_scalar(double *p, double v) { *p = v; }
 // ---------------------------------------------------------------------------------------
 // setup: geometry from node coordinates with the reference's formulas (src/Bathymetry.cpp)
 // ---------------------------------------------------------------------------------------
-__global__ void k_setup_cells(int nt, const int *tp, const int *tt, const double4 *node, double4 *cgeo, double *area) {
+__global__ void k_setup_cells(int nt, const int *tp, const int *tt, const double4 *node, double4 *cgeo, double *area, double *cb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
     const double4 P0 = node[tp[i]], P1 = node[tp[nt + i]], P2 = node[tp[2 * nt + i]];
@@ -435,6 +581,7 @@ __global__ void k_setup_cells(int nt, const int *tp, const int *tt, const double
     const bool bnd = (tt[i] | tt[nt + i] | tt[2 * nt + i]) < 0;
     g.w = bnd ? __longlong_as_double(0x7ff0000000000000ll) : smax(smax(P0.z, P1.z), P2.z);
     cgeo[i] = g;
+    cb[i] = g.z;
     const double ax = P1.x - P0.x, ay = P1.y - P0.y, bx = P2.x - P0.x, by = P2.y - P0.y;
     area[i] = 0.5 * fabs(ax * by - bx * ay);  // Domain::Area (:87-90)
 }
@@ -504,7 +651,7 @@ __global__ void k_flux_out(int ne, const int *old, const double *f0, const doubl
 }
 // edge-side taps into the reference's EdgeField layout: column 2e + (from < to), caller ids
 // (include/ValueField.h:70-75). which = 0: (w,u,v) of m_edg, 1: (0, sx, sy) of m_src.
-__global__ void k_edge_out(DevMesh m, DevFields s, const int *cell_old, const int *edge_old, int which, double *aos) {
+__global__ void k_edge_out(DevMesh m, DevFields s, const int *cell_old, const int *edge_old, int which, double cor, double *aos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nt = m.nt;
     if (i >= nt) return;
@@ -520,25 +667,28 @@ __global__ void k_edge_out(DevMesh m, DevFields s, const int *cell_old, const in
         if (which == 0) {
             aos[3 * col] = s.cew[slot]; aos[3 * col + 1] = s.ceu[slot]; aos[3 * col + 2] = s.cev[slot];
         } else {
-            aos[3 * col] = 0.; aos[3 * col + 1] = s.csx[slot]; aos[3 * col + 2] = s.csy[slot];
+            aos[3 * col] = 0.;
+            aos[3 * col + 1] = s.cgx[i] + cor * (-s.cev[slot]);
+            aos[3 * col + 2] = s.cgy[i] + cor * s.ceu[slot];
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// halo pack / unpack (multi-GPU): component-major buffers [3][n]
+// halo pack / unpack (multi-GPU): buffers hold (w,u,v) per listed cell, buf[3k + c], so the
+// segment of each peer is contiguous
 // ---------------------------------------------------------------------------------------
 __global__ void k_halo_pack(int n, const int *cells, const double *w, const double *u, const double *v, double *buf) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int c = cells[k];
-    buf[k] = w[c]; buf[n + k] = u[c]; buf[2 * (size_t)n + k] = v[c];
+    buf[3 * (size_t)k] = w[c]; buf[3 * (size_t)k + 1] = u[c]; buf[3 * (size_t)k + 2] = v[c];
 }
 __global__ void k_halo_unpack(int n, const int *cells, const double *buf, double *w, double *u, double *v) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int c = cells[k];
-    w[c] = buf[k]; u[c] = buf[n + k]; v[c] = buf[2 * (size_t)n + k];
+    w[c] = buf[3 * (size_t)k]; u[c] = buf[3 * (size_t)k + 1]; v[c] = buf[3 * (size_t)k + 2];
 }
 
 // ---------------------------------------------------------------------------------------

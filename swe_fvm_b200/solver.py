@@ -111,6 +111,19 @@ class SpaceDisc:
         self._call("swe_get_time", C.byref(v))
         return v.value
 
+    def kernel_timing(self, enable: bool = True):
+        self._call("swe_kernel_timing", int(enable))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total ms, launches)} recorded since kernel_timing(True)."""
+        ms = np.zeros(16)
+        cnt = np.zeros(16, dtype=np.int64)
+        names = (C.c_char_p * 16)()
+        k = capi.lib().swe_kernel_times(self._ctx, 16, capi.dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64)), names)
+        if k < 0:
+            capi.check(k, self._ctx)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
+
     def launch_count(self) -> int:
         return int(capi.lib().swe_launch_count(self._ctx))
 
