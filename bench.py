@@ -36,8 +36,12 @@ B_PER_CELL_UPDATE_SSPRK2 = 1488.0  # 744 B per cell-stage x 2 
 # (every array element counted once per kernel that needs it, structured
 # ratios Ne/Nt = 1.5, Nn/Nt = 0.5)
 KERNEL_BYTES_PER_CELL = {
-    "k_stage_begin": 8.0, "k_reconstruct": 221.0, "k_partwet2": 1.0, "k_flux": 156.0, "k_drain": 56.0,
-    "k_update": 264.0,
+    "k_reconstruct": 185.0,  # W 24 + tt,tp 24 + cgeo 32 + nodes 16 | ceh,ceu,cev 72 + cgx,cgy 16 + cls 1
+    "k_partwet2": 0.0,       # work list only (O(sqrt N) part-wet cells)
+    "k_flux": 156.0,         # per edge: slots 8 + n 16 + dmin 8 + two sides 48 | F 24; x 1.5 edges per cell
+    "k_drain": 56.0,         # te 12 + F0 12 + w 8 + cb 8 + area 8 | dti 8
+    "k_update": 220.0,       # W 24 + (U0 24 on the 2nd stage) + te,tt 24 + F 36 + dti 8 + ceh 24 + grad 16 + n 24 +
+                             # L 12 + area 8 + cb 8 | W 24  -> 208 (stage 1) / 232 (stage 2), mean 220
 }
 
 
@@ -314,7 +318,8 @@ def run_gpu(args):
     dom_bytes = KERNEL_BYTES_PER_CELL[dom] * mesh.nt
     achieved = dom_bytes / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9
     kern = {k: {"ms_per_launch": (v[0] / v[1] if v[1] else 0.0), "launches": v[1], "share": v[0] / tot_kms,
-                "alg_GBps": (KERNEL_BYTES_PER_CELL[k] * mesh.nt / (v[0] / v[1] * 1e-3) / 1e9 if v[1] and v[0] > 0 else 0.0)}
+                "alg_GBps": (KERNEL_BYTES_PER_CELL[k] * mesh.nt / (v[0] / v[1] * 1e-3) / 1e9 if v[1] and v[0] > 0 else 0.0),
+                "alg_bytes_per_cell": KERNEL_BYTES_PER_CELL[k]}
             for k, v in ktimes.items()}
     step_gbps = value / world * B_PER_CELL_UPDATE_SSPRK2 / 1e9
     # CPU baseline: the oracle, 1 thread (the reference is single-threaded), bounded sample
@@ -346,7 +351,7 @@ def run_gpu(args):
                               "frac": step_gbps / peak, "per": "GPU"},
                      "kernels": kern},
         "cpu_baseline": cpu,
-        "mass_drift_rel": (d1["mass"] - d0["mass"]) / d0["mass"] if d0["mass"] else 0.0,
+        "mass_drift_rel": ((d1["mass"] - d0["mass"]) / d0["mass"] if d0["mass"] else 0.0) if world == 1 else None,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
