@@ -45,6 +45,11 @@ KERNEL_BYTES_PER_CELL = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# profiles/r1_v2_ncu_full_summary.csv (64M-cell fully-wet workload); None for other workloads
+NCU_TRAFFIC_BYTES_64M = {"k_reconstruct": 13.320e9, "k_flux": 11.539e9, "k_drain": 3.749e9, "k_update": 13.953e9}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -211,7 +216,7 @@ def run_gpu(args):
         n_owned = dec.n_owned
         length_y = 4.0 * world
     case, v0 = build_case(args.case, mesh, 0.5 * length_y, 4.0)
-    sd = SpaceDisc("hllc", "einfeldt", mesh, None, device=local_rank, reorder=False)
+    sd = SpaceDisc("hllc", "einfeldt", mesh, None, device=local_rank, reorder=args.reorder)
     sd.set_stream(torch.cuda.current_stream().cuda_stream)
     td = TimeDisc(sd)
     pin_in = torch.from_numpy(v0).pin_memory()
@@ -338,14 +343,17 @@ def run_gpu(args):
                    "cells_per_gpu": int(n_owned), "cells_total": int(cells_total),
                    "l2": "inputs larger than L2 (state + edge fields >> 126 MB), no flush needed",
                    "parallelism": "1 GPU" if world == 1 else f"{world} strips, 3-row halo, NCCL send/recv + min all-reduce",
-                   "dt": "CFLdt of the previous step (device resident)", "setup_s": t_setup},
+                   "dt": "CFLdt of the previous step (device resident)", "setup_s": t_setup,
+                   "device_numbering": "morton" if args.reorder else "caller"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(24 * mesh.nt), "d2h_bytes_per_step": int(24 * mesh.nt),
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 "what": "per step: swe_set_state_async(pinned host) + swe_step + swe_get_state_async(pinned host)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": (NCU_TRAFFIC_BYTES_64M.get(dom) if (args.n == 4096 and args.case == "fully_wet") else None),
+                     "traffic_source": "ncu --set full, profiles/r1_v2_ncu_full_summary.csv", "peak_source": peak_src,
                      "alg_bytes_per_launch": dom_bytes,
                      "step": {"alg_bytes_per_cell_update": B_PER_CELL_UPDATE_SSPRK2, "achieved": step_gbps,
                               "frac": step_gbps / peak, "per": "GPU"},
@@ -370,6 +378,9 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reorder", action="store_true",
+                    help="Morton-renumber cells/edges/nodes on the device (A/B-measured on this structured "
+                         "workload: no gain over the generator's row-major numbering, so off by default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

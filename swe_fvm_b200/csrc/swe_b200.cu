@@ -17,6 +17,8 @@
 #include "hostmesh.hpp"
 #include "swe_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 using namespace swe;
 
 struct swe_ctx {
@@ -131,18 +133,42 @@ static inline uint64_t spread21(uint64_t x) {
     x = (x | x << 2) & 0x1249249249249249ull;
     return x;
 }
-static void morton_order(const std::vector<double> &x, const std::vector<double> &y, double x0, double y0,
-                         double sx, double sy, std::vector<int> &newid) {
+// Morton order of n points: keys are built on the host (OpenMP), the stable key sort runs on the
+// device (CUB radix sort, set-up only; ties keep the caller's order, so the result is the same
+// as a host std::sort of (key, index) pairs). newid[old] = position in Morton order.
+static cudaError_t morton_order(const std::vector<double> &x, const std::vector<double> &y, double x0, double y0,
+                                double sx, double sy, std::vector<int> &newid) {
     const size_t n = x.size();
-    std::vector<std::pair<uint64_t, int>> keys(n);
-    for (size_t i = 0; i < n; ++i) {
+    std::vector<uint64_t> keys(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
         uint64_t qx = (uint64_t)std::min(2097151.0, std::max(0.0, (x[i] - x0) * sx));
         uint64_t qy = (uint64_t)std::min(2097151.0, std::max(0.0, (y[i] - y0) * sy));
-        keys[i] = {spread21(qx) | (spread21(qy) << 1), (int)i};
+        keys[i] = spread21(qx) | (spread21(qy) << 1);
     }
-    std::sort(keys.begin(), keys.end());
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    uint64_t *dk_in = nullptr, *dk_out = nullptr;
+    int *dv_in = nullptr, *dv_out = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() { cudaFree(dk_in); cudaFree(dk_out); cudaFree(dv_in); cudaFree(dv_out); cudaFree(tmp); };
+#define MO_TRY(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
+    MO_TRY(cudaMalloc(&dk_in, n * 8)); MO_TRY(cudaMalloc(&dk_out, n * 8));
+    MO_TRY(cudaMalloc(&dv_in, n * 4)); MO_TRY(cudaMalloc(&dv_out, n * 4));
+    MO_TRY(cudaMemcpy(dk_in, keys.data(), n * 8, cudaMemcpyHostToDevice));
+    MO_TRY(cudaMemcpy(dv_in, order.data(), n * 4, cudaMemcpyHostToDevice));
+    MO_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 42));
+    MO_TRY(cudaMalloc(&tmp, tmp_bytes));
+    MO_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 42));
+    MO_TRY(cudaMemcpy(order.data(), dv_out, n * 4, cudaMemcpyDeviceToHost));
+#undef MO_TRY
+    cleanup();
     newid.resize(n);
-    for (size_t k = 0; k < n; ++k) newid[keys[k].second] = (int)k;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)n; ++k) newid[order[k]] = (int)k;
+    return cudaSuccess;
 }
 
 static void destroy_ctx(swe_ctx *c) {
@@ -253,17 +279,17 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
                 xs[t] = (mesh->geometry[3 * q[0]] + mesh->geometry[3 * q[1]] + mesh->geometry[3 * q[2]]) / 3.;
                 ys[t] = (mesh->geometry[3 * q[0] + 1] + mesh->geometry[3 * q[1] + 1] + mesh->geometry[3 * q[2] + 1]) / 3.;
             }
-            morton_order(xs, ys, x0, y0, sc, sc, cell_new);
+            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, cell_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
             xs.resize((size_t)ne); ys.resize((size_t)ne);
             for (int64_t e = 0; e < ne; ++e) {
                 const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
                 xs[e] = 0.5 * (mesh->geometry[3 * a] + mesh->geometry[3 * b]);
                 ys[e] = 0.5 * (mesh->geometry[3 * a + 1] + mesh->geometry[3 * b + 1]);
             }
-            morton_order(xs, ys, x0, y0, sc, sc, edge_new);
+            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, edge_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
             xs.resize((size_t)nn); ys.resize((size_t)nn);
             for (int64_t p = 0; p < nn; ++p) { xs[p] = mesh->geometry[3 * p]; ys[p] = mesh->geometry[3 * p + 1]; }
-            morton_order(xs, ys, x0, y0, sc, sc, node_new);
+            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, node_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
         } else {
             cell_new.resize((size_t)nt); std::iota(cell_new.begin(), cell_new.end(), 0);
             edge_new.resize((size_t)ne); std::iota(edge_new.begin(), edge_new.end(), 0);

@@ -1,0 +1,127 @@
+"""GPU parity at BASELINE.json's configurations and size-independent properties at full size.
+
+configs[0] LakeAtRest 20 164 cells is in test_gpu_parity.py. Here:
+configs[1] ClassicThacker, StructTriangMesh(512) = 1 048 576 cells, HLLC<Einfeldt>, SSPRK2
+configs[2] bowl.msh refined 4x = 3 785 728 cells, paraboloid bed, HLLC<Einfeldt>, SSPRK2
+configs[3] 67 108 864 cells on one GPU: mass conservation, lake at rest, symmetry (no oracle run)
+plus the 10^4-step drift bound of the north star (1e-9 relative L2; we get equality).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, make_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(mesh, v0, reorder=False):
+    from swe_fvm_b200.solver import SpaceDisc, TimeDisc
+    from oracle.oracle import Oracle
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0, reorder=reorder)
+    ref = Oracle(mesh, threads=0)  # all host threads; OpenMP oracle == scalar oracle (tested on CPU)
+    ref.set_state(v0)
+    return sd, TimeDisc(sd), ref
+
+
+def test_config1_thacker_1m_cells():
+    """1e-12 relative L2 per step is the bar (north star); the kernels give equality."""
+    from swe_fvm_b200.solver import Solvers
+    mesh, case, v0 = make_case("classic_thacker", 512, quad_n=2)
+    assert mesh.nt == 1048576
+    sd, td, ref = _pair(mesh, v0)
+    dt = 2e-4
+    for k in range(6):
+        Solvers.SSPRK2(td, dt)
+        ref.step(1, 1, 2, dt)
+        got, want = sd.GetVolField(), ref.get_state()
+        assert rel_l2(got, want) <= 1e-12
+        dt = td.CFLdt()
+        assert dt == ref.cfl_dt()
+    np.testing.assert_array_equal(got, want)
+    cls = sd.cell_class()
+    assert (cls == 1).sum() > 0 and (cls == 2).sum() > 0 and (cls == 0).sum() > 0.8 * mesh.nt  # wet/dry front present
+
+
+def test_config2_bowl_refined_4x():
+    from swe_fvm_b200 import TriangMesh
+    from swe_fvm_b200.solver import Solvers
+    m = TriangMesh.from_gmsh(os.path.join(GOLDEN, "bowl.msh"))
+    for _ in range(4):
+        m = m.refine()
+    assert (m.nt, m.ne, m.nn) == (3785728, 5681152, 1895425)
+    mesh, case, v0 = make_case("bowl_hump", mesh=m, level=3.0, amp=0.5)
+    sd, td, ref = _pair(mesh, v0, reorder=True)
+    m0 = sd.diagnostics()["mass"]
+    dt = 1e-4
+    for k in range(4):
+        Solvers.SSPRK2(td, dt)
+        ref.step(1, 1, 2, dt)
+        dt = td.CFLdt()
+        assert dt == ref.cfl_dt()
+    got, want = sd.GetVolField(), ref.get_state()
+    assert rel_l2(got, want) <= 1e-12
+    np.testing.assert_array_equal(got, want)
+    assert abs(sd.diagnostics()["mass"] - m0) <= 1e-13 * m0
+
+
+def test_drift_after_1e4_steps():
+    """North star: within 1e-9 after 10^4 steps with a moving wet/dry front."""
+    from swe_fvm_b200.solver import Solvers
+    mesh, case, v0 = make_case("classic_thacker", 32, quad_n=8)
+    sd, td, ref = _pair(mesh, v0)
+    m0 = sd.diagnostics()["mass"]
+    Solvers.run(td, "ssprk2", 10000, dt=1e-3)
+    ref.run(1, 1, 2, 10000, 1e-3)
+    got, want = sd.GetVolField(), ref.get_state()
+    assert np.isfinite(got).all()
+    assert rel_l2(got, want) <= 1e-9
+    np.testing.assert_array_equal(got, want)
+    assert abs(sd.diagnostics()["mass"] - m0) <= 1e-12 * m0
+    assert abs(sd.time() - 10.0) < 1e-9
+
+
+def test_config3_full_size_properties():
+    """67M cells (the bench workload size): mass conserved to round-off over CFL-sized steps with
+    a moving shoreline, depth stays non-negative, and a host round trip (swe_get_state ->
+    swe_set_state) in the middle of a run changes nothing (bitwise)."""
+    from swe_fvm_b200 import Case, StructTriangMesh
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    n = 4096
+    mesh = StructTriangMesh(n, n, 4.0 / n)
+    case = Case("classic_thacker", 2.0, 2.0, 4.0)
+    case.set_bathymetry(mesh)
+    v0 = case.initial_state(mesh, quad_n=1)
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0)
+    td = TimeDisc(sd)
+    d0 = sd.diagnostics()
+    Solvers.run(td, "ssprk2", 20, dt=2e-5)
+    sd.synchronize()
+    d1 = sd.diagnostics()
+    assert abs(d1["mass"] - d0["mass"]) <= 1e-12 * d0["mass"]
+    assert d1["hmin"] >= 0.0 and np.isfinite(d1["vmax"]) and d1["vmax"] > 0
+    assert 0 < d1["wet_cells"] < 0.2 * mesh.nt
+    straight = sd.GetVolField()
+    sd.SetVolField(v0)
+    Solvers.run(td, "ssprk2", 10, dt=2e-5)
+    mid = sd.GetVolField()
+    sd.SetVolField(mid)
+    Solvers.run(td, "ssprk2", 10, dt=2e-5)
+    np.testing.assert_array_equal(sd.GetVolField(), straight)
+    # the dry part of the basin is untouched: w == cell bed exactly, zero velocity
+    dry = sd.cell_class() == 0
+    cb = mesh.centroids()[:, 2]
+    assert (straight[dry, 0] == cb[dry]).all() and (straight[dry, 1:] == 0).all()
+
+
+def test_lake_at_rest_full_size_strip():
+    """Well-balancing at scale: a 16M-cell lake at rest over the step bump stays at rest."""
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    mesh, case, v0 = make_case("lake_at_rest", 2048, quad_n=1)
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0)
+    Solvers.run(TimeDisc(sd), "ssprk3", 50, dt=1e-4)
+    d = sd.diagnostics()
+    assert d["vmax"] <= 1e-13
+    got = sd.GetVolField()
+    assert np.abs(got[:, 0]).max() <= 1e-13
