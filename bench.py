@@ -230,7 +230,7 @@ def run_gpu(args):
     SSPRK2 = 1
     if dec is not None:
         local = swd.GpuLocal(sd)
-        solver = swd.DistributedSolver(dec, local)
+        solver = swd.DistributedSolver(dec, local, overlap=not args.no_overlap)
 
         def run_steps(k):
             solver.run(SSPRK2, k, None, dt0=dt_first[0])
@@ -285,6 +285,7 @@ def run_gpu(args):
         sd.set_state_async(pin_in.data_ptr())
         if dec is not None:
             solver.step(SSPRK2, dt_e2e)
+            solver.finish()
         else:
             Solvers.SSPRK2(td, dt_e2e)
         sd.get_state_async(pin_in.data_ptr())
@@ -342,7 +343,8 @@ def run_gpu(args):
         "config": {"workload": workload_name(args, world), "wet_cell_fraction": wet_frac,
                    "cells_per_gpu": int(n_owned), "cells_total": int(cells_total),
                    "l2": "inputs larger than L2 (state + edge fields >> 126 MB), no flush needed",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} strips, 3-row halo, NCCL send/recv + min all-reduce",
+                   "parallelism": "1 GPU" if world == 1 else (f"{world} strips, 3-row halo, NCCL send/recv "
+                                   f"{'overlapped with interior reconstruction' if solver.overlap else '(not overlapped)'} + min all-reduce"),
                    "dt": "CFLdt of the previous step (device resident)", "setup_s": t_setup,
                    "device_numbering": "morton" if args.reorder else "caller"},
         "clocks": clocks,
@@ -378,6 +380,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange with interior work")
     ap.add_argument("--reorder", action="store_true",
                     help="Morton-renumber cells/edges/nodes on the device (A/B-measured on this structured "
                          "workload: no gain over the generator's row-major numbering, so off by default)")

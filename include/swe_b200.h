@@ -133,6 +133,13 @@ SWE_API int swe_kernel_times(swe_ctx *ctx, int32_t max_kinds, double *ms_total, 
 /* The two halves of a stage, callable on their own (parity taps, custom TimeDisc loops). */
 SWE_API int swe_compute_interface_values(swe_ctx *ctx);
 SWE_API int swe_compute_fluxes(swe_ctx *ctx, swe_flux flux, swe_wavespeed ws);
+/* ComputeInterfaceValues split by cell range [first_cell, last_cell) so that a multi-GPU driver
+ * can reconstruct the interior while the halo is still in flight and the boundary rows after it
+ * arrived. begin != 0 on the first range of a stage, finish != 0 on the last one (runs the
+ * part-wet second pass, which needs every first-pass result). Caller numbering; requires a
+ * context created with reorder = 0. */
+SWE_API int swe_compute_interface_values_range(swe_ctx *ctx, int64_t first_cell, int64_t last_cell,
+                                               int begin, int finish);
 /* stage update: cons(i) = a0*U0.cons(i) + a1*cons(i) + RHS(i, dt_stage), U0 = state saved by
  * swe_save_state(). Euler: a0=0,a1=1. Uses the fluxes of the last swe_compute_fluxes. */
 SWE_API int swe_save_state(swe_ctx *ctx);

@@ -84,6 +84,7 @@ SYMBOLS = {
     "swe_kernel_times": (C.c_int, [_P, C.c_int32, _D, _I64, C.POINTER(C.c_char_p)]),
     "swe_compute_interface_values": (C.c_int, [_P]),
     "swe_compute_fluxes": (C.c_int, [_P, C.c_int, C.c_int]),
+    "swe_compute_interface_values_range": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "swe_save_state": (C.c_int, [_P]),
     "swe_stage_update": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "swe_stage_update_dev": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),

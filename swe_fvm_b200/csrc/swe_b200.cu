@@ -484,25 +484,43 @@ SWE_API int swe_enable_taps(swe_ctx *c, int on) {
     return SWE_OK;
 }
 
-SWE_API int swe_compute_interface_values(swe_ctx *c) {
-    if (!c) return SWE_ERR_INVALID;
+// pass 1 on the cell range [first, last) (DEVICE numbering = caller numbering when the context
+// was created with reorder = 0). begin: reset the part-wet work list; finish: run pass 2.
+static int interface_values_range(swe_ctx *c, int first, int last, bool begin, bool finish) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     int rc;
-    CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, 2 * sizeof(int), c->stream));  // part-wet list + K1 tile counters
-    int kt = kt_begin(c, KT_RECONSTRUCT);
-    // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
-    const int g1 = (SWE_K1_MODE == 0) ? nblk(c->nt, kBlock) : std::min(nblk(c->nt, kBlock), c->sms * SWE_K1_GRID_PER_SM);
-    if (c->taps) k_reconstruct<true><<<g1, kBlock, 0, c->stream>>>(m, s);
-    else k_reconstruct<false><<<g1, kBlock, 0, c->stream>>>(m, s);
-    kt_end(c, kt);
-    if ((rc = launch_check(c, "k_reconstruct"))) return rc;
-    kt = kt_begin(c, KT_PARTWET2);
-    if (c->taps) k_partwet2<true><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
-    else k_partwet2<false><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
-    kt_end(c, kt);
-    return launch_check(c, "k_partwet2");
+    if (begin) CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, 2 * sizeof(int), c->stream));  // part-wet list counter
+    if (last > first) {
+        int kt = kt_begin(c, KT_RECONSTRUCT);
+        // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
+        const int g1 = std::min(nblk(last - first, kBlock), c->sms * SWE_K1_GRID_PER_SM);
+        if (c->taps) k_reconstruct<true><<<g1, kBlock, 0, c->stream>>>(m, s, first, last);
+        else k_reconstruct<false><<<g1, kBlock, 0, c->stream>>>(m, s, first, last);
+        kt_end(c, kt);
+        if ((rc = launch_check(c, "k_reconstruct"))) return rc;
+    }
+    if (finish) {
+        int kt = kt_begin(c, KT_PARTWET2);
+        if (c->taps) k_partwet2<true><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
+        else k_partwet2<false><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
+        kt_end(c, kt);
+        return launch_check(c, "k_partwet2");
+    }
+    return SWE_OK;
+}
+
+SWE_API int swe_compute_interface_values(swe_ctx *c) {
+    if (!c) return SWE_ERR_INVALID;
+    return interface_values_range(c, 0, c->nt, true, true);
+}
+
+SWE_API int swe_compute_interface_values_range(swe_ctx *c, int64_t first_cell, int64_t last_cell, int begin, int finish) {
+    if (!c) return SWE_ERR_INVALID;
+    if (c->reordered) { c->err = "swe_compute_interface_values_range: needs a context created with reorder = 0"; return SWE_ERR_INVALID; }
+    if (first_cell < 0 || last_cell > c->nt || first_cell > last_cell) { c->err = "swe_compute_interface_values_range: bad range"; return SWE_ERR_INVALID; }
+    return interface_values_range(c, (int)first_cell, (int)last_cell, begin != 0, finish != 0);
 }
 
 SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {

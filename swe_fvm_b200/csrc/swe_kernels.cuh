@@ -96,16 +96,12 @@ __device__ __forceinline__ double muscl_w_at(const Muscl &M, double cx, double c
 // K1: classification + pass-1 reconstruction of every cell (src/SpaceDisc.cpp:37-45,
 // src/MUSCLObject.cpp:13-112). Part-wet cells are appended to the pass-2 work list.
 // ---------------------------------------------------------------------------------------
-// K1 dispatch (SWE_K1_MODE): 0 = one block per 128-cell tile, hardware in-order dispatch keeps
-// the active window of the mesh compact (best L1/L2 reuse of the shared nodes / neighbours);
-// 1 = persistent grid-stride with next-cell id prefetch; 2 = persistent warps pulling 128-cell
-// tiles in order from an atomic counter (compact window + id prefetch).
-// A cp.async (LDGSTS) double-buffered variant that staged all 36 inputs of a cell in shared
-// memory was measured slower (5.1 ms vs 3.5 ms at 64M cells: profiles/r1_k1_cpasync_*): the
-// 221 KB of smem leaves no L1 and persistent blocks drift apart, doubling DRAM reads.
-#ifndef SWE_K1_MODE
-#define SWE_K1_MODE 1
-#endif
+// K1 dispatch: persistent grid-stride, exactly one resident wave (3 CTAs/SM at ~160 registers).
+// Measured alternatives that were slower at 64M cells (profiles/README.md): one CTA per 128-cell
+// tile (3.78 vs 3.30 ms), in-order atomic tile dispatch (3.66), register caps that spill (5.2-5.9),
+// shared-memory parking of the neighbour states for 16-20 warps/SM (3.55-3.69), a cp.async (LDGSTS)
+// double-buffered smem staging of all 36 inputs (5.1: no L1 left beside 221 KB smem and
+// persistent CTAs drift apart), register-free prefetch.global of the next cell's gathers (3.68).
 #ifndef SWE_K1_MIN_BLOCKS
 #define SWE_K1_MIN_BLOCKS 3
 #endif
@@ -228,221 +224,27 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
     emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mxk[2], myk[2], mbk[2]);
 }
 
-#ifndef SWE_K1_PARK
-#define SWE_K1_PARK 0
-#endif
-#if SWE_K1_PARK
-// Register-lean variant: the neighbour states N[3][3] and the node coordinates are parked in
-// the thread's private shared-memory slots right after they arrive and re-read at their points
-// of use (solve, limiter, emit), so fewer doubles are live across the fp64 section.
-struct K1Park {
-    volatile double *base;  // [18][kBlock]
-    __device__ __forceinline__ void put(int v, double x) const { base[v * kBlock + threadIdx.x] = x; }
-    __device__ __forceinline__ double get(int v) const { return base[v * kBlock + threadIdx.x]; }
-};
+// persistent grid-stride kernel over the cell range [first, last); the ids of the thread's next
+// cell are fetched before the current cell is processed (hides the first memory round trip)
 template <bool TAPS>
-__device__ __forceinline__ void reconstruct_cell_parked(const DevMesh &m, const DevFields &s, const K1Park &pk, const int i,
-                                                        const int ip0, const int ip1, const int ip2, const int it0,
-                                                        const int it1, const int it2) {
+__global__ void __launch_bounds__(kBlock, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s, int first, int last) {
     const int nt = m.nt;
-    const int jt[3] = {max(it0, 0), max(it1, 0), max(it2, 0)};
-    double w, u, v, cx, cy, cb;
-    bool dry, full;
-    double bmax, bmin;
-    double4 Gn[3];
-    {
-        const double4 P0 = ldg4(m.node + ip0), P1 = ldg4(m.node + ip1), P2 = ldg4(m.node + ip2);
-        const double4 Gi = ldg4(m.cgeo + i);
-        w = __ldg(s.w + i); u = __ldg(s.u + i); v = __ldg(s.v + i);
-        double N[3][3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            N[k][0] = __ldg(s.w + jt[k]); N[k][1] = __ldg(s.u + jt[k]); N[k][2] = __ldg(s.v + jt[k]);
-            Gn[k] = ldg4(m.cgeo + jt[k]);
-        }
-        cx = Gi.x; cy = Gi.y; cb = Gi.z;
-        pk.put(0, P0.x); pk.put(1, P0.y); pk.put(2, P0.z);
-        pk.put(3, P1.x); pk.put(4, P1.y); pk.put(5, P1.z);
-        pk.put(6, P2.x); pk.put(7, P2.y); pk.put(8, P2.z);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { pk.put(9 + 3 * k, N[k][0]); pk.put(10 + 3 * k, N[k][1]); pk.put(11 + 3 * k, N[k][2]); }
-        bmax = smax(smax(P0.z, P1.z), P2.z);
-        bmin = smin(smin(P0.z, P1.z), P2.z);
-    }
-#define PX(k) pk.get(3 * (k))
-#define PY(k) pk.get(3 * (k) + 1)
-#define PZ(k) pk.get(3 * (k) + 2)
-#define NB(k, c) pk.get(9 + 3 * (k) + (c))
-#define MX(k) (0.5 * (PX(k) + PX(((k) + 1) % 3)))
-#define MY(k) (0.5 * (PY(k) + PY(((k) + 1) % 3)))
-#define MB(k) (0.5 * (PZ(k) + PZ(((k) + 1) % 3)))
-    const bool bnd = (it0 | it1 | it2) < 0;
-    dry = !is_wet(w - cb);
-    full = !bnd && (bmax < w);
-    s.cls[i] = dry ? 0 : (full ? 2 : 1);
-
-    Muscl M;
-    M.g00 = M.g01 = M.g10 = M.g11 = M.g20 = M.g21 = 0.;
-    if (dry) {
-        M.o0 = cb; M.o1 = 0.; M.o2 = 0.;
-        gradient3(PX(0), PY(0), PZ(0), PX(1), PY(1), PZ(1), PX(2), PY(2), PZ(2), M.g00, M.g01);
-    } else if (!full) {
-        M.o0 = partwet1_level(w, cb, bmax, bmin); M.o1 = u; M.o2 = v;
-        s.pw_list[atomicAdd(&s.flags[1], 1)] = i;
-    } else {
-        M.o0 = w; M.o1 = u; M.o2 = v;
-        // classification of the neighbours and support points
-        double X[3][2];
-        bool zero_grad = false;
-        unsigned pwmask = 0;  // neighbours that are part-wet (rare): V is patched below
-        double A[3][3];       // their PartWet1 values at the shared edge midpoint (only if pwmask)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double wj = NB(k, 0);
-            const double4 Gj = Gn[k];
-            if (Gj.w < wj) {
-                X[k][0] = Gj.x; X[k][1] = Gj.y;
-            } else if (!is_wet(wj - Gj.z)) {
-                zero_grad = true;
-                X[k][0] = X[k][1] = 0.;
-            } else {
-                const int j = jt[k];
-                const double z0 = m.node[m.tp[j]].z, z1 = m.node[m.tp[nt + j]].z, z2 = m.node[m.tp[2 * nt + j]].z;
-                const double b13 = smax(smax(z0, z1), z2), b23 = smin(smin(z0, z1), z2);
-                double a0 = partwet1_level(wj, Gj.z, b13, b23), a1 = NB(k, 1), a2 = NB(k, 2);
-                const double mx = MX(k), my = MY(k), mb = MB(k);
-                const double dx = mx - Gj.x, dy = my - Gj.y;
-                a0 = a0 + (0. * dx + 0. * dy); a1 = a1 + (0. * dx + 0. * dy); a2 = a2 + (0. * dx + 0. * dy);
-                if (!((a0 - mb) >= 0)) { a0 = mb; a1 = 0.; a2 = 0.; }
-                X[k][0] = mx; X[k][1] = my;
-                A[k][0] = a0; A[k][1] = a1; A[k][2] = a2;
-                pwmask |= 1u << k;
-            }
-        }
-        if (!zero_grad) {
-            const Lu2 lu = lu2_factor(X[0][0], X[0][1], X[1][0], X[1][1], X[2][0], X[2][1]);
-            const double own[3] = {w, u, v};
-            double df[3][2];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double V0 = NB(0, c), V1 = NB(1, c), V2 = NB(2, c);
-                if (pwmask) {
-                    if (pwmask & 1u) V0 = 0.5 * (own[c] + A[0][c]);
-                    if (pwmask & 2u) V1 = 0.5 * (own[c] + A[1][c]);
-                    if (pwmask & 4u) V2 = 0.5 * (own[c] + A[2][c]);
-                }
-                lu2_solve(lu, V0, V1, V2, df[c][0], df[c][1]);
-            }
-            {   // vertex positivity (:66-72): dx = P(ip) * (I - 1/3), evaluated literally
-                const double md = 1. - 1. / 3., mo = 0. - 1. / 3.;
-                const double x0 = PX(0), x1 = PX(1), x2 = PX(2), y0 = PY(0), y1 = PY(1), y2 = PY(2);
-                const double dx0 = (x0 * md + x1 * mo) + x2 * mo, dy0 = (y0 * md + y1 * mo) + y2 * mo;
-                const double dx1 = (x0 * mo + x1 * md) + x2 * mo, dy1 = (y0 * mo + y1 * md) + y2 * mo;
-                const double dx2 = (x0 * mo + x1 * mo) + x2 * md, dy2 = (y0 * mo + y1 * mo) + y2 * md;
-                const double hp0 = ((df[0][0] * dx0 + df[0][1] * dy0) + w) - PZ(0);
-                const double hp1 = ((df[0][0] * dx1 + df[0][1] * dy1) + w) - PZ(1);
-                const double hp2 = ((df[0][0] * dx2 + df[0][1] * dy2) + w) - PZ(2);
-                if (!(is_wet(hp0) && is_wet(hp1) && is_wet(hp2))) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) df[c][0] = df[c][1] = 0.;
-                }
-            }
-            double tvd[3] = {1., 1., 1.};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double dx = MX(k) - cx, dy = MY(k) - cy;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const double nb = NB(k, c);
-                    const double lo = smin(own[c], nb), hi = smax(own[c], nb);
-                    const double vek = own[c] + (df[c][0] * dx + df[c][1] * dy);
-                    if (!((lo <= vek) && (vek <= hi))) tvd[c] = 0.;
-                }
-            }
-            M.g00 = tvd[0] * df[0][0]; M.g01 = tvd[0] * df[0][1];
-            M.g10 = tvd[1] * df[1][0]; M.g11 = tvd[1] * df[1][1];
-            M.g20 = tvd[2] * df[2][0]; M.g21 = tvd[2] * df[2][1];
-        }
-    }
-    s.cgx[i] = M.g00; s.cgy[i] = M.g01;
-    emit_edge<TAPS>(s, i, M, cx, cy, MX(0), MY(0), MB(0));
-    emit_edge<TAPS>(s, nt + i, M, cx, cy, MX(1), MY(1), MB(1));
-    emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, MX(2), MY(2), MB(2));
-#undef PX
-#undef PY
-#undef PZ
-#undef NB
-#undef MX
-#undef MY
-#undef MB
-}
-#endif
-
-template <bool TAPS>
-__global__ void __launch_bounds__(kBlock, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s) {
-    const int nt = m.nt;
-#if SWE_K1_MODE == 0
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nt) return;
-    reconstruct_cell<TAPS>(m, s, i, __ldg(m.tp + i), __ldg(m.tp + nt + i), __ldg(m.tp + 2 * nt + i), __ldg(m.tt + i),
-                           __ldg(m.tt + nt + i), __ldg(m.tt + 2 * nt + i));
-#elif SWE_K1_MODE == 1
-#if SWE_K1_PARK
-    __shared__ double k1_park[18 * kBlock];
-    K1Park pk;
-    pk.base = k1_park;
-#endif
     const int stride = gridDim.x * blockDim.x;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nt) return;
+    int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= last) return;
     int ip0 = __ldg(m.tp + i), ip1 = __ldg(m.tp + nt + i), ip2 = __ldg(m.tp + 2 * nt + i);
     int it0 = __ldg(m.tt + i), it1 = __ldg(m.tt + nt + i), it2 = __ldg(m.tt + 2 * nt + i);
     for (;;) {
         const int nx = i + stride;
         int np0 = 0, np1 = 0, np2 = 0, nt0 = 0, nt1 = 0, nt2 = 0;
-        if (nx < nt) {
+        if (nx < last) {
             np0 = __ldg(m.tp + nx); np1 = __ldg(m.tp + nt + nx); np2 = __ldg(m.tp + 2 * nt + nx);
             nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
         }
-#if SWE_K1_PARK
-        reconstruct_cell_parked<TAPS>(m, s, pk, i, ip0, ip1, ip2, it0, it1, it2);
-#else
         reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
-#endif
-        if (nx >= nt) break;
+        if (nx >= last) break;
         i = nx; ip0 = np0; ip1 = np1; ip2 = np2; it0 = nt0; it1 = nt1; it2 = nt2;
     }
-#else
-    // every warp pulls 128-cell tiles in order from flags[2] (reset before the launch)
-    const int lane = threadIdx.x & 31;
-    const int ntiles = (nt + 127) >> 7;
-    int tile = 0;
-    if (lane == 0) tile = atomicAdd(&s.flags[2], 1);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    while (tile < ntiles) {
-        int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&s.flags[2], 1);  // in flight while this tile is processed
-        const int base = (tile << 7) + lane;
-        int i = base;
-        int ip0 = 0, ip1 = 0, ip2 = 0, it0 = 0, it1 = 0, it2 = 0;
-        if (i < nt) {
-            ip0 = __ldg(m.tp + i); ip1 = __ldg(m.tp + nt + i); ip2 = __ldg(m.tp + 2 * nt + i);
-            it0 = __ldg(m.tt + i); it1 = __ldg(m.tt + nt + i); it2 = __ldg(m.tt + 2 * nt + i);
-        }
-#pragma unroll 1
-        for (int sub = 0; sub < 4; ++sub) {
-            const int nx = base + 32 * (sub + 1);
-            int np0 = 0, np1 = 0, np2 = 0, nt0 = 0, nt1 = 0, nt2 = 0;
-            if (sub < 3 && nx < nt) {
-                np0 = __ldg(m.tp + nx); np1 = __ldg(m.tp + nt + nx); np2 = __ldg(m.tp + 2 * nt + nx);
-                nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
-            }
-            if (i < nt) reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
-            i = nx; ip0 = np0; ip1 = np1; ip2 = np2; it0 = nt0; it1 = nt1; it2 = nt2;
-        }
-        tile = __shfl_sync(0xffffffffu, nxt, 0);
-    }
-#endif
 }
 
 // Value at node Q = (qx, qy, qz) of cell t's PASS-1 reconstruction, i.e. one term of the max in

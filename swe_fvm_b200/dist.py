@@ -32,6 +32,9 @@ class Decomposition:
     owned: np.ndarray                   # bool (nt_local)
     global_cells: np.ndarray | None     # int64 (nt_local) or None for strips (implicit)
     peers: list = field(default_factory=list)   # [(peer, send_local_ids, recv_local_ids)] sorted by peer
+    # local cell range [a, b) whose reconstruction stencil touches no halo cell (None: unknown); the
+    # halo exchange of the previous stage is overlapped with the reconstruction of this range
+    interior: tuple | None = None
 
     @property
     def n_owned(self) -> int:
@@ -87,7 +90,11 @@ def decompose_strips(ni: int, nj: int, h: float, rank: int, world: int, halo_row
     if rank < world - 1:
         pj0, pj1 = rows[rank + 1]
         peers.append((rank + 1, row_cells(max(j0, j1 - halo_rows), j1), row_cells(j1, min(pj1, j1 + halo_rows))))
-    return Decomposition(mesh, rank, world, owned, None, peers)
+    # cells of the halo rows and of the owned row next to them read halo states in K1
+    a = (halo_rows + 1) * cells_per_row if rank > 0 else 0
+    b = mesh.nt - ((halo_rows + 1) * cells_per_row if rank < world - 1 else 0)
+    interior = (a, b) if (world > 1 and b > a) else None
+    return Decomposition(mesh, rank, world, owned, None, peers, interior)
 
 
 def decompose_general(global_mesh: TriangMesh, part: np.ndarray, rank: int, world: int,
@@ -135,9 +142,7 @@ class HaloExchanger:
         local.set_halo_lists(dec.send_list(), dec.recv_list())
         self.bytes_per_exchange = 8 * 3 * (self.nsend + self.nrecv)
 
-    def exchange(self):
-        if not self.dec.peers:
-            return
+    def _post(self):
         import torch.distributed as dist
         self.local.pack(self.sendbuf)
         ops, so, ro = [], 0, 0
@@ -152,6 +157,27 @@ class HaloExchanger:
             req.wait()
         self.local.unpack(self.recvbuf)
 
+    def exchange(self):
+        """Blocking (in stream order) exchange on the solver's own stream."""
+        if self.dec.peers:
+            self._post()
+
+    def start(self):
+        """Asynchronous exchange on a side stream (CUDA only): pack -> send/recv -> unpack run
+        concurrently with whatever the main stream does next; finish() orders the main stream
+        after it."""
+        if not self.dec.peers:
+            return
+        self.local.begin_side_stream()
+        try:
+            self._post()
+        finally:
+            self.local.end_side_stream()
+
+    def finish(self):
+        if self.dec.peers:
+            self.local.wait_side_stream()
+
 
 class DistributedSolver:
     """Solvers::{Euler,SSPRK2,SSPRK3} across ranks: the per-stage pieces of the C-ABI plus one
@@ -163,12 +189,27 @@ class DistributedSolver:
         2: [(0.0, 1.0, 1.0), (0.75, 0.25, 0.25), (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0)],
     }
 
-    def __init__(self, dec: Decomposition, local):
+    def __init__(self, dec: Decomposition, local, overlap: bool | None = None):
         self.dec, self.local = dec, local
         self.halo = HaloExchanger(dec, local)
         local.set_cfl_edge_mask(dec.cfl_edge_mask())
         self.exchanges = 0
         self.allreduces = 0
+        can = dec.interior is not None and getattr(local, "supports_overlap", False)
+        self.overlap = can if overlap is None else (overlap and can)
+        self._pending = False
+
+    def _interface_values(self):
+        L = self.local
+        if not self._pending:
+            L.compute_interface_values()
+            return
+        a, b = self.dec.interior
+        L.compute_interface_values_range(a, b, True, False)   # overlaps the halo exchange in flight
+        self.halo.finish()
+        self._pending = False
+        L.compute_interface_values_range(0, a, False, False)
+        L.compute_interface_values_range(b, self.dec.mesh.nt, False, True)
 
     def step(self, scheme: int, dt: float | None):
         """dt None: adaptive, dt = 0.15 * global min_len of the previous step's last stage
@@ -177,7 +218,7 @@ class DistributedSolver:
         L = self.local
         stages = self.STAGES[scheme]
         for k, (a0, a1, coef) in enumerate(stages):
-            L.compute_interface_values()
+            self._interface_values()
             L.compute_fluxes()
             if k == len(stages) - 1 and self.dec.world > 1:
                 dist.all_reduce(L.min_len_tensor(), op=dist.ReduceOp.MIN)
@@ -185,19 +226,32 @@ class DistributedSolver:
             if k == 0 and len(stages) > 1:
                 L.save_state()
             L.stage_update(a0, a1, coef, dt)
-            self.halo.exchange()
+            if self.overlap:
+                self.halo.start()
+                self._pending = True
+            else:
+                self.halo.exchange()
             self.exchanges += 1
         L.advance_dt(dt)
+
+    def finish(self):
+        """Order the main stream after an exchange that is still in flight."""
+        if self._pending:
+            self.halo.finish()
+            self._pending = False
 
     def run(self, scheme: int, nsteps: int, dt: float | None, dt0: float = 0.0):
         if dt is None:
             self.local.set_dt(dt0)
         for _ in range(nsteps):
             self.step(scheme, dt)
+        self.finish()
 
 
 class GpuLocal:
     """The device context of this rank, driven through the per-stage C-ABI entry points."""
+
+    supports_overlap = True
 
     def __init__(self, sd):
         import torch
@@ -205,6 +259,34 @@ class GpuLocal:
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._minlen = None
+        self._main = torch.cuda.current_stream()
+        self._side = None
+        self._ev_main = torch.cuda.Event()
+        self._ev_side = torch.cuda.Event()
+        self._ctx_mgr = None
+        sd.set_stream(self._main.cuda_stream)
+
+    # -- side stream for the overlapped halo exchange --
+    def begin_side_stream(self):
+        if self._side is None:
+            self._side = self.torch.cuda.Stream()
+        self._ev_main.record(self._main)
+        self._side.wait_event(self._ev_main)
+        self._ctx_mgr = self.torch.cuda.stream(self._side)
+        self._ctx_mgr.__enter__()
+        self.sd.set_stream(self._side.cuda_stream)
+
+    def end_side_stream(self):
+        self._ev_side.record(self._side)
+        self.sd.set_stream(self._main.cuda_stream)
+        self._ctx_mgr.__exit__(None, None, None)
+        self._ctx_mgr = None
+
+    def wait_side_stream(self):
+        self._main.wait_event(self._ev_side)
+
+    def compute_interface_values_range(self, first, last, begin, finish):
+        self.sd._call("swe_compute_interface_values_range", int(first), int(last), int(begin), int(finish))
 
     def alloc(self, n):
         return self.torch.empty(n, dtype=self.torch.float64, device=self.device)

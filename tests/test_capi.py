@@ -73,5 +73,6 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not pat.search(txt), (f, pat.search(txt).group(0))
-    for f in os.listdir(os.path.join(ROOT, "include")):
-        assert not pat.search(open(os.path.join(ROOT, "include", f)).read())
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
+        for f in files:
+            assert not pat.search(open(os.path.join(dirpath, f)).read()), f
