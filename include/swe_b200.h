@@ -253,6 +253,16 @@ SWE_API int swe_case_set_bathymetry(const swe_case *c, swe_hostmesh *m);
 SWE_API int swe_case_initial_state(const swe_case *c, const swe_hostmesh *m, int32_t quad_n,
                                    double t, double *prim_3xnt);
 
+/* The same on the device (no host loop, for 10^7-10^8 cells): nodal bathymetry b(x,y) written
+ * into the context's node array (and the bed-dependent cell geometry refreshed), the cell state
+ * built by TriangAverage<3, quad_n> on the device, and the L2 error of (h, hu, hv) against the
+ * exact solution at time t sampled at the centroids (upstream's commented CompareWith,
+ * src/SpaceDisc.cpp:106-138). Device libm differs from glibc in the last ulp, so device-built
+ * states are inputs in their own right. */
+SWE_API int swe_case_set_bathymetry_device(swe_ctx *ctx, const swe_case *c);
+SWE_API int swe_case_initial_state_device(swe_ctx *ctx, const swe_case *c, int32_t quad_n, double t);
+SWE_API int swe_case_l2_error(swe_ctx *ctx, const swe_case *c, double t, double out[3]);
+
 SWE_API const char *swe_version(void);
 
 #ifdef __cplusplus

@@ -119,6 +119,9 @@ SYMBOLS = {
     "swe_case_eval": (C.c_int, [C.POINTER(CaseStruct), C.c_double, C.c_double, C.c_double, _D]),
     "swe_case_set_bathymetry": (C.c_int, [C.POINTER(CaseStruct), _P]),
     "swe_case_initial_state": (C.c_int, [C.POINTER(CaseStruct), _P, C.c_int32, C.c_double, _D]),
+    "swe_case_set_bathymetry_device": (C.c_int, [_P, C.POINTER(CaseStruct)]),
+    "swe_case_initial_state_device": (C.c_int, [_P, C.POINTER(CaseStruct), C.c_int32, C.c_double]),
+    "swe_case_l2_error": (C.c_int, [_P, C.POINTER(CaseStruct), C.c_double, _D]),
     "swe_version": (C.c_char_p, []),
 }
 

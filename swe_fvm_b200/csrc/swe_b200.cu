@@ -16,6 +16,7 @@
 #include "../../include/swe_b200.h"
 #include "hostmesh.hpp"
 #include "swe_kernels.cuh"
+#include "swe_cases.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -767,6 +768,40 @@ SWE_API int swe_kernel_times(swe_ctx *c, int32_t max_kinds, double *ms_total, in
         ms_total[p.id] += ms; counts[p.id]++;
     }
     return KT_COUNT;
+}
+
+// ---- analytic cases on the device ----
+SWE_API int swe_case_set_bathymetry_device(swe_ctx *c, const swe_case *cs) {
+    if (!c || !cs || cs->kind < 0 || cs->kind > SWE_CASE_BOWL_HUMP) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_case_bathymetry<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->node, *cs);
+    int rc;
+    if ((rc = launch_check(c, "k_case_bathymetry"))) return rc;
+    // geometry that depends on the bed: cgeo (cb, bfull) and cb
+    k_setup_cells<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->tp, c->tt, c->node, c->cgeo, c->area, c->cb);
+    return launch_check(c, "k_setup_cells");
+}
+SWE_API int swe_case_initial_state_device(swe_ctx *c, const swe_case *cs, int32_t quad_n, double t) {
+    if (!c || !cs || quad_n < 1 || cs->kind < 0 || cs->kind > SWE_CASE_BOWL_HUMP) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_case_init<<<nblk(c->nt, 128), 128, 0, c->stream>>>(dev_mesh(c), *cs, quad_n, t, c->cur[0], c->cur[1], c->cur[2]);
+    int rc;
+    if ((rc = launch_check(c, "k_case_init"))) return rc;
+    k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal + 2, t);
+    CUDA_TRY(c, cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));
+    return launch_check(c, "k_set_scalar");
+}
+SWE_API int swe_case_l2_error(swe_ctx *c, const swe_case *cs, double t, double out[3]) {
+    if (!c || !cs || !out || cs->kind < 0 || cs->kind > SWE_CASE_BOWL_HUMP) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_case_error_partial<<<kDiagBlocks, kDiagThreads, 0, c->stream>>>(dev_mesh(c), dev_fields(c), *cs, t, c->diag);
+    int rc;
+    if ((rc = launch_check(c, "k_case_error_partial"))) return rc;
+    k_case_error_final<<<1, 32, 0, c->stream>>>(c->diag, c->diag + 6 * kDiagBlocks);
+    if ((rc = launch_check(c, "k_case_error_final"))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->diag + 6 * kDiagBlocks, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
 }
 
 // ---- multi-GPU support ----

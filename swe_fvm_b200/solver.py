@@ -106,6 +106,19 @@ class SpaceDisc:
         out = self._get("swe_diagnostics", (6,))
         return dict(mass=out[0], kinetic=out[1], potential=out[2], vmax=out[3], hmin=out[4], wet_cells=int(out[5]))
 
+    # -- analytic cases on the device (initial state / error norms without host loops) --
+    def set_case_bathymetry(self, case):
+        self._call("swe_case_set_bathymetry_device", C.byref(case.c))
+
+    def set_case_state(self, case, quad_n: int = 4, t: float = 0.0):
+        self._call("swe_case_initial_state_device", C.byref(case.c), int(quad_n), float(t))
+
+    def case_l2_error(self, case, t: float) -> np.ndarray:
+        """L2 error of (h, hu, hv) against the exact solution at time t."""
+        out = np.empty(3)
+        self._call("swe_case_l2_error", C.byref(case.c), float(t), capi.dptr(out))
+        return out
+
     def time(self) -> float:
         v = C.c_double()
         self._call("swe_get_time", C.byref(v))

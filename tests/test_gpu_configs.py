@@ -125,3 +125,35 @@ def test_lake_at_rest_full_size_strip():
     assert d["vmax"] <= 1e-13
     got = sd.GetVolField()
     assert np.abs(got[:, 0]).max() <= 1e-13
+
+
+def test_device_side_cases_match_host():
+    """§8 f2/f3: bathymetry + TriangAverage initial state + L2 error norm computed on the device
+    agree with the host path to round-off (device libm vs glibc), and the Thacker error after a
+    short run matches the host-evaluated norm."""
+    from swe_fvm_b200 import Case, StructTriangMesh
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    n = 96
+    for kind in ("classic_thacker", "fully_wet", "lake_at_rest", "bowl_hump"):
+        mesh = StructTriangMesh(n, n, 4.0 / n)
+        case = Case(kind, 2.0, 2.0, 4.0)
+        sd = SpaceDisc("hllc", "einfeldt", mesh, None)   # bed = 0 at creation
+        sd.set_case_bathymetry(case)
+        sd.set_case_state(case, quad_n=6)
+        dev = sd.GetVolField()
+        case.set_bathymetry(mesh)
+        host = case.initial_state(mesh, quad_n=6)
+        assert np.abs(dev - host).max() <= 1e-12, kind
+    mesh, case, v0 = make_case("classic_thacker", n, quad_n=6)
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0)
+    td = TimeDisc(sd)
+    Solvers.run(td, "ssprk2", 100, dt=1e-3)
+    t = sd.time()
+    err = sd.case_l2_error(case, t)
+    q, cen, A = sd.GetVolField(), mesh.centroids(), mesh.areas()
+    ex = np.array([case.eval(x, y, t) for x, y in cen[:, :2]])
+    h = q[:, 0] - cen[:, 2]
+    want = [np.sqrt((A * (h - ex[:, 1]) ** 2).sum()), np.sqrt((A * (h * q[:, 1] - ex[:, 1] * ex[:, 2]) ** 2).sum()),
+            np.sqrt((A * (h * q[:, 2] - ex[:, 1] * ex[:, 3]) ** 2).sum())]
+    assert np.allclose(err, want, rtol=1e-9, atol=1e-14)
+    assert err[0] < 1e-2
