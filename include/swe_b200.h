@@ -87,9 +87,16 @@ typedef struct swe_mesh {
 /* ------------------------------------------------------------------------------------ */
 typedef struct swe_ctx swe_ctx;
 
-/* reorder: 0 = keep caller numbering on device, 1 = locality-preserving (Morton) renumbering
+/* reorder: 0 = keep caller numbering on device, 1 = locality-preserving (Hilbert curve) renumbering
  * of cells/edges/nodes on device. Results and every get/set use the CALLER's numbering. */
 SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reorder);
+/* Same, with an ordering class (0..3) per cell: cells of one class get one contiguous range of
+ * device ids (inside it: Hilbert order if reorder != 0, caller order otherwise), so that
+ * swe_compute_interface_values_class can reconstruct class by class. A multi-GPU driver puts the
+ * cells whose stencil touches halo cells in their own class and overlaps the halo exchange with
+ * the reconstruction of all the others. */
+SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, int reorder,
+                               const uint8_t *cell_class_nt);
 SWE_API void swe_destroy(swe_ctx *ctx);
 /* message of the last failure on ctx (ctx may be NULL: last failure of swe_create/hostmesh). */
 SWE_API const char *swe_last_error(const swe_ctx *ctx);
@@ -140,6 +147,8 @@ SWE_API int swe_compute_fluxes(swe_ctx *ctx, swe_flux flux, swe_wavespeed ws);
  * context created with reorder = 0. */
 SWE_API int swe_compute_interface_values_range(swe_ctx *ctx, int64_t first_cell, int64_t last_cell,
                                                int begin, int finish);
+/* the same for all cells of one ordering class (see swe_create_classes) */
+SWE_API int swe_compute_interface_values_class(swe_ctx *ctx, int32_t cell_class, int begin, int finish);
 /* stage update: cons(i) = a0*U0.cons(i) + a1*cons(i) + RHS(i, dt_stage), U0 = state saved by
  * swe_save_state(). Euler: a0=0,a1=1. Uses the fluxes of the last swe_compute_fluxes. */
 SWE_API int swe_save_state(swe_ctx *ctx);

@@ -66,6 +66,7 @@ _U8 = C.POINTER(C.c_uint8)
 _I8 = C.POINTER(C.c_int8)
 SYMBOLS = {
     "swe_create": (C.c_int, [C.POINTER(_P), C.POINTER(MeshStruct), C.c_int, C.c_int]),
+    "swe_create_classes": (C.c_int, [C.POINTER(_P), C.POINTER(MeshStruct), C.c_int, C.c_int, _U8]),
     "swe_destroy": (None, [_P]),
     "swe_last_error": (C.c_char_p, [_P]),
     "swe_set_stream": (C.c_int, [_P, _P]),
@@ -85,6 +86,7 @@ SYMBOLS = {
     "swe_compute_interface_values": (C.c_int, [_P]),
     "swe_compute_fluxes": (C.c_int, [_P, C.c_int, C.c_int]),
     "swe_compute_interface_values_range": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "swe_compute_interface_values_class": (C.c_int, [_P, C.c_int32, C.c_int, C.c_int]),
     "swe_save_state": (C.c_int, [_P]),
     "swe_stage_update": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "swe_stage_update_dev": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),

@@ -32,6 +32,7 @@ struct swe_ctx {
     double cor = 0, tau = 0;
     bool reordered = false;
     bool taps = false;
+    int class_first[6] = {0, 0, 0, 0, 0, 0};  // device cell range of every ordering class
     // device mesh
     int *tt = nullptr, *te = nullptr, *tp = nullptr, *slotL = nullptr, *slotR = nullptr;
     double4 *cgeo = nullptr, *node = nullptr;
@@ -124,28 +125,35 @@ static int launch_check(swe_ctx *c, const char *what) {
     return SWE_OK;
 }
 
-// Morton key of a point in the unit square (21 bits per axis)
-static inline uint64_t spread21(uint64_t x) {
-    x &= 0x1fffff;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
+// Hilbert-curve index of a point on the 2^21 x 2^21 grid (locality-preserving renumbering; no
+// quadrant jumps, unlike the Z-order / Morton curve)
+static inline uint64_t hilbert21(uint64_t x, uint64_t y) {
+    const uint64_t n = 1ull << 21;
+    uint64_t d = 0;
+    for (uint64_t s = n >> 1; s > 0; s >>= 1) {
+        const uint64_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        d += s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = n - 1 - x; y = n - 1 - y; }
+            const uint64_t t = x; x = y; y = t;
+        }
+    }
+    return d;
 }
-// Morton order of n points: keys are built on the host (OpenMP), the stable key sort runs on the
+// Space-filling-curve order of n points: keys are built on the host (OpenMP), the stable key sort runs on the
 // device (CUB radix sort, set-up only; ties keep the caller's order, so the result is the same
 // as a host std::sort of (key, index) pairs). newid[old] = position in Morton order.
 static cudaError_t morton_order(const std::vector<double> &x, const std::vector<double> &y, double x0, double y0,
-                                double sx, double sy, std::vector<int> &newid) {
+                                double sx, double sy, std::vector<int> &newid, const uint8_t *cls = nullptr,
+                                bool curve = true) {
     const size_t n = x.size();
     std::vector<uint64_t> keys(n);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         uint64_t qx = (uint64_t)std::min(2097151.0, std::max(0.0, (x[i] - x0) * sx));
         uint64_t qy = (uint64_t)std::min(2097151.0, std::max(0.0, (y[i] - y0) * sy));
-        keys[i] = spread21(qx) | (spread21(qy) << 1);
+        keys[i] = curve ? hilbert21(qx, qy) : (uint64_t)i;  // curve off: keep the caller's order inside a class
+        if (cls) keys[i] |= (uint64_t)cls[i] << 42;
     }
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
@@ -160,9 +168,9 @@ static cudaError_t morton_order(const std::vector<double> &x, const std::vector<
     MO_TRY(cudaMalloc(&dv_in, n * 4)); MO_TRY(cudaMalloc(&dv_out, n * 4));
     MO_TRY(cudaMemcpy(dk_in, keys.data(), n * 8, cudaMemcpyHostToDevice));
     MO_TRY(cudaMemcpy(dv_in, order.data(), n * 4, cudaMemcpyHostToDevice));
-    MO_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 42));
+    MO_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 45));
     MO_TRY(cudaMalloc(&tmp, tmp_bytes));
-    MO_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 42));
+    MO_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 45));
     MO_TRY(cudaMemcpy(order.data(), dv_out, n * 4, cudaMemcpyDeviceToHost));
 #undef MO_TRY
     cleanup();
@@ -216,7 +224,7 @@ SWE_API const char *swe_last_error(const swe_ctx *ctx) {
     return swe::host_error();
 }
 
-SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reorder) {
+SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, int reorder, const uint8_t *cell_class) {
     g_create_error.clear();
     auto fail = [&](int code, const std::string &msg) { g_create_error = msg; return code; };
     if (!out || !mesh) return fail(SWE_ERR_INVALID, "swe_create: null argument");
@@ -261,7 +269,10 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
     if (!c) return fail(SWE_ERR_NOMEM, "out of host memory");
     c->device = device; c->nt = (int)nt; c->ne = (int)ne; c->nn = (int)nn; c->sms = sm_count;
     c->cor = mesh->cor; c->tau = mesh->tau;
-    c->reordered = reorder != 0;
+    c->reordered = reorder != 0 || cell_class != nullptr;
+    if (cell_class)
+        for (int64_t t = 0; t < nt; ++t)
+            if (cell_class[t] > 3) { delete c; return fail(SWE_ERR_INVALID, "swe_create_classes: class ids must be 0..3"); }
 
     // ---- numbering: caller id -> device id ----
     std::vector<int> cell_new, edge_new, node_new;
@@ -280,7 +291,8 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
                 xs[t] = (mesh->geometry[3 * q[0]] + mesh->geometry[3 * q[1]] + mesh->geometry[3 * q[2]]) / 3.;
                 ys[t] = (mesh->geometry[3 * q[0] + 1] + mesh->geometry[3 * q[1] + 1] + mesh->geometry[3 * q[2] + 1]) / 3.;
             }
-            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, cell_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
+            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, cell_new, cell_class, reorder != 0)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
+            if (reorder != 0) {
             xs.resize((size_t)ne); ys.resize((size_t)ne);
             for (int64_t e = 0; e < ne; ++e) {
                 const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
@@ -291,6 +303,10 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
             xs.resize((size_t)nn); ys.resize((size_t)nn);
             for (int64_t p = 0; p < nn; ++p) { xs[p] = mesh->geometry[3 * p]; ys[p] = mesh->geometry[3 * p + 1]; }
             if ((ce = morton_order(xs, ys, x0, y0, sc, sc, node_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
+            } else {
+                edge_new.resize((size_t)ne); std::iota(edge_new.begin(), edge_new.end(), 0);
+                node_new.resize((size_t)nn); std::iota(node_new.begin(), node_new.end(), 0);
+            }
         } else {
             cell_new.resize((size_t)nt); std::iota(cell_new.begin(), cell_new.end(), 0);
             edge_new.resize((size_t)ne); std::iota(edge_new.begin(), edge_new.end(), 0);
@@ -298,6 +314,12 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
         }
     } catch (const std::bad_alloc &) { delete c; return fail(SWE_ERR_NOMEM, "out of host memory"); }
     c->cell_new = cell_new;
+    {   // device range of every ordering class (one class = everything when none are given)
+        int counts[5] = {0, 0, 0, 0, 0};
+        if (cell_class) for (int64_t t = 0; t < nt; ++t) counts[cell_class[t]]++; else counts[0] = (int)nt;
+        c->class_first[0] = 0;
+        for (int q = 0; q < 5; ++q) c->class_first[q + 1] = c->class_first[q] + counts[q];
+    }
 
 #define CREATE_TRY(call)                                                                          \
     do {                                                                                          \
@@ -420,6 +442,10 @@ SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reor
     return SWE_OK;
 }
 
+SWE_API int swe_create(swe_ctx **out, const swe_mesh *mesh, int device, int reorder) {
+    return swe_create_classes(out, mesh, device, reorder, nullptr);
+}
+
 SWE_API void swe_destroy(swe_ctx *ctx) { destroy_ctx(ctx); }
 
 SWE_API int swe_set_stream(swe_ctx *c, void *stream) {
@@ -496,9 +522,9 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
     if (last > first) {
         int kt = kt_begin(c, KT_RECONSTRUCT);
         // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
-        const int g1 = std::min(nblk(last - first, kBlock), c->sms * SWE_K1_GRID_PER_SM);
-        if (c->taps) k_reconstruct<true><<<g1, kBlock, 0, c->stream>>>(m, s, first, last);
-        else k_reconstruct<false><<<g1, kBlock, 0, c->stream>>>(m, s, first, last);
+        const int g1 = std::min(nblk(last - first, kK1Block), c->sms * SWE_K1_GRID_PER_SM);
+        if (c->taps) k_reconstruct<true><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last);
+        else k_reconstruct<false><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last);
         kt_end(c, kt);
         if ((rc = launch_check(c, "k_reconstruct"))) return rc;
     }
@@ -515,6 +541,11 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
 SWE_API int swe_compute_interface_values(swe_ctx *c) {
     if (!c) return SWE_ERR_INVALID;
     return interface_values_range(c, 0, c->nt, true, true);
+}
+
+SWE_API int swe_compute_interface_values_class(swe_ctx *c, int32_t cls, int begin, int finish) {
+    if (!c || cls < 0 || cls > 3) return SWE_ERR_INVALID;
+    return interface_values_range(c, c->class_first[cls], c->class_first[cls + 1], begin != 0, finish != 0);
 }
 
 SWE_API int swe_compute_interface_values_range(swe_ctx *c, int64_t first_cell, int64_t last_cell, int begin, int finish) {

@@ -51,6 +51,19 @@ struct DevFields {
 
 constexpr int kBlock = 128;
 
+// stores of write-once intermediates (edge-side values, gradients, fluxes, dti) may carry the
+// evict-first hint so that they do not displace the gathered neighbour data in L2 (SWE_STCS=1)
+#ifndef SWE_STCS
+#define SWE_STCS 0
+#endif
+__device__ __forceinline__ void st_once(double *p, double v) {
+#if SWE_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // MUSCL::AtPoint (include/MUSCLObject.h:26-33) for one component set
 struct Muscl {
     double o0, o1, o2;
@@ -78,7 +91,7 @@ __device__ __forceinline__ void emit_edge(const DevFields &s, int slot, const Mu
             eu *= fac; ev *= fac;
         }
     }
-    s.ceh[slot] = eh; s.ceu[slot] = eu; s.cev[slot] = ev;
+    st_once(s.ceh + slot, eh); st_once(s.ceu + slot, eu); st_once(s.cev + slot, ev);
     if (TAPS) s.cew[slot] = ew;
     // m_src (src/SpaceDisc.cpp:26-29) = Gradient(edge).row(0) + cor * (-v_e, u_e). MUSCL::Gradient(p)
     // (include/MUSCLObject.h:41-48) always evaluates to m_grad: when the reconstructed depth is
@@ -102,6 +115,10 @@ __device__ __forceinline__ double muscl_w_at(const Muscl &M, double cx, double c
 // shared-memory parking of the neighbour states for 16-20 warps/SM (3.55-3.69), a cp.async (LDGSTS)
 // double-buffered smem staging of all 36 inputs (5.1: no L1 left beside 221 KB smem and
 // persistent CTAs drift apart), register-free prefetch.global of the next cell's gathers (3.68).
+#ifndef SWE_K1_BLOCK
+#define SWE_K1_BLOCK 128
+#endif
+constexpr int kK1Block = SWE_K1_BLOCK;
 #ifndef SWE_K1_MIN_BLOCKS
 #define SWE_K1_MIN_BLOCKS 3
 #endif
@@ -218,7 +235,7 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
         }
     }
     // UpdateInterfaceValues (src/SpaceDisc.cpp:15-31); the node maxima (:23) are gathered in pass 2
-    s.cgx[i] = M.g00; s.cgy[i] = M.g01;
+    st_once(s.cgx + i, M.g00); st_once(s.cgy + i, M.g01);
     emit_edge<TAPS>(s, i, M, cx, cy, mxk[0], myk[0], mbk[0]);
     emit_edge<TAPS>(s, nt + i, M, cx, cy, mxk[1], myk[1], mbk[1]);
     emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mxk[2], myk[2], mbk[2]);
@@ -227,7 +244,7 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
 // persistent grid-stride kernel over the cell range [first, last); the ids of the thread's next
 // cell are fetched before the current cell is processed (hides the first memory round trip)
 template <bool TAPS>
-__global__ void __launch_bounds__(kBlock, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s, int first, int last) {
+__global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s, int first, int last) {
     const int nt = m.nt;
     const int stride = gridDim.x * blockDim.x;
     int i = first + blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,7 +414,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
                                        __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand);
                 if (m.cfl_mask == nullptr || m.cfl_mask[e]) l2w = (cand < l2w) ? cand : l2w;
             }
-            s.f0[e] = f0; s.f1[e] = f1; s.f2[e] = f2;
+            st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
             if (nx >= ne) break;
             e = nx; sl = nsl; sr = nsr;
         }
@@ -447,7 +464,7 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
         }
         r = (sum > kTol) ? m.area[i] * h / sum : __longlong_as_double(0x7ff0000000000000ll);
     }
-    s.dti[i] = r;
+    st_once(s.dti + i, r);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -48,6 +48,21 @@ class Decomposition:
         m[has] |= self.owned[et[has, 1]]
         return m.astype(np.uint8)
 
+    def cell_classes(self) -> np.ndarray:
+        """Ordering class per local cell for swe_create_classes: 1 = the reconstruction stencil
+        (the cell and its three edge neighbours) contains a halo cell, 0 = it does not, so class 0
+        can be reconstructed while the halo exchange of the previous stage is still in flight."""
+        halo = np.zeros(self.mesh.nt, dtype=bool)
+        if self.peers:
+            halo[self.recv_list()] = True
+        tt = self.mesh.element_neighbours
+        dep = halo.copy()
+        for k in range(3):
+            j = tt[:, k]
+            ok = j >= 0
+            dep[ok] |= halo[j[ok]]
+        return dep.astype(np.uint8)
+
     def send_list(self) -> np.ndarray:
         return np.concatenate([p[1] for p in self.peers]) if self.peers else np.zeros(0, np.int64)
 
@@ -195,7 +210,7 @@ class DistributedSolver:
         local.set_cfl_edge_mask(dec.cfl_edge_mask())
         self.exchanges = 0
         self.allreduces = 0
-        can = dec.interior is not None and getattr(local, "supports_overlap", False)
+        can = bool(dec.peers) and getattr(local, "supports_overlap", False) and getattr(local, "has_classes", False)
         self.overlap = can if overlap is None else (overlap and can)
         self._pending = False
 
@@ -204,12 +219,10 @@ class DistributedSolver:
         if not self._pending:
             L.compute_interface_values()
             return
-        a, b = self.dec.interior
-        L.compute_interface_values_range(a, b, True, False)   # overlaps the halo exchange in flight
+        L.compute_interface_values_class(0, True, False)   # overlaps the halo exchange in flight
         self.halo.finish()
         self._pending = False
-        L.compute_interface_values_range(0, a, False, False)
-        L.compute_interface_values_range(b, self.dec.mesh.nt, False, True)
+        L.compute_interface_values_class(1, False, True)
 
     def step(self, scheme: int, dt: float | None):
         """dt None: adaptive, dt = 0.15 * global min_len of the previous step's last stage
@@ -253,9 +266,10 @@ class GpuLocal:
 
     supports_overlap = True
 
-    def __init__(self, sd):
+    def __init__(self, sd, has_classes: bool = False):
         import torch
         self.sd = sd
+        self.has_classes = has_classes  # sd was created with cell_class = dec.cell_classes()
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._minlen = None
@@ -285,8 +299,8 @@ class GpuLocal:
     def wait_side_stream(self):
         self._main.wait_event(self._ev_side)
 
-    def compute_interface_values_range(self, first, last, begin, finish):
-        self.sd._call("swe_compute_interface_values_range", int(first), int(last), int(begin), int(finish))
+    def compute_interface_values_class(self, cls, begin, finish):
+        self.sd._call("swe_compute_interface_values_class", int(cls), int(begin), int(finish))
 
     def alloc(self, n):
         return self.torch.empty(n, dtype=self.torch.float64, device=self.device)

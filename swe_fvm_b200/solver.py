@@ -22,7 +22,8 @@ from .mesh import TriangMesh
 
 class SpaceDisc:
     def __init__(self, flux: str | int, wavespeed: str | int, mesh: TriangMesh, v0: np.ndarray | None = None,
-                 cor: float = 0.0, tau: float = 0.0, device: int = 0, reorder: bool = False, taps: bool = False):
+                 cor: float = 0.0, tau: float = 0.0, device: int = 0, reorder: bool = False, taps: bool = False,
+                 cell_class: np.ndarray | None = None):
         self.flux = capi.FLUXES[flux.lower()] if isinstance(flux, str) else int(flux)
         self.wavespeed = capi.WAVESPEEDS[wavespeed.lower()] if isinstance(wavespeed, str) else int(wavespeed)
         self.mesh = mesh
@@ -30,7 +31,14 @@ class SpaceDisc:
         self.cor, self.tau = float(cor), float(tau)
         self._ctx = C.c_void_p()
         cm = mesh.c_mesh(cor, tau)
-        capi.check(capi.lib().swe_create(C.byref(self._ctx), C.byref(cm), device, int(reorder)))
+        if cell_class is None:
+            capi.check(capi.lib().swe_create(C.byref(self._ctx), C.byref(cm), device, int(reorder)))
+        else:
+            cc = np.ascontiguousarray(cell_class, dtype=np.uint8)
+            if cc.shape != (self.nt,):
+                raise ValueError("cell_class must have one entry per cell")
+            capi.check(capi.lib().swe_create_classes(C.byref(self._ctx), C.byref(cm), device, int(reorder),
+                                                     cc.ctypes.data_as(C.POINTER(C.c_uint8))))
         if taps:
             self._call("swe_enable_taps", 1)
         if v0 is not None:

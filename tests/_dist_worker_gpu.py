@@ -36,9 +36,10 @@ def main():
         gids = dec.global_cells
     case.set_bathymetry(dec.mesh)
     v0 = case.initial_state(dec.mesh, quad_n=4)
-    sd = SpaceDisc("hllc", "einfeldt", dec.mesh, v0, device=local_rank, reorder=(mode != "strips"))
+    sd = SpaceDisc("hllc", "einfeldt", dec.mesh, v0, device=local_rank, reorder=(mode != "strips"),
+                   cell_class=dec.cell_classes())
     sd.set_stream(torch.cuda.current_stream().cuda_stream)
-    local = swd.GpuLocal(sd)
+    local = swd.GpuLocal(sd, has_classes=True)
     solver = swd.DistributedSolver(dec, local)
     solver.run(scheme, nsteps, None if adaptive else 2e-3, dt0=1e-3)
     sd.synchronize()
