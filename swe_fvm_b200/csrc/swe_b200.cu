@@ -48,7 +48,7 @@ struct swe_ctx {
     double *ceh = nullptr, *ceu = nullptr, *cev = nullptr, *cgx = nullptr, *cgy = nullptr, *cew = nullptr;
     double *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *dti = nullptr;
     signed char *cls = nullptr;
-    int *pw_list = nullptr;
+    int *pw_list = nullptr, *rs_list = nullptr;
     double *scal = nullptr;
     int *flags = nullptr;
     double *diag = nullptr;  // partials + 6 outputs
@@ -110,7 +110,7 @@ static DevFields dev_fields(const swe_ctx *c) {
     DevFields s;
     s.w = c->cur[0]; s.u = c->cur[1]; s.v = c->cur[2];
     s.ceh = c->ceh; s.ceu = c->ceu; s.cev = c->cev; s.cgx = c->cgx; s.cgy = c->cgy; s.cew = c->cew;
-    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.cls = c->cls; s.pw_list = c->pw_list;
+    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.cls = c->cls; s.pw_list = c->pw_list; s.rs_list = c->rs_list;
     s.scal = c->scal; s.flags = c->flags;
     return s;
 }
@@ -186,7 +186,7 @@ static void destroy_ctx(swe_ctx *c) {
     void *ptrs[] = {c->tt, c->te, c->tp, c->slotL, c->slotR, c->cgeo, c->node, c->en, c->area, c->cb, c->elen, c->dmin,
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
-                    c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->scal, c->flags, c->diag, c->stage_aos,
+                    c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
                     c->send_cells, c->recv_cells};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &p : c->kt_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -418,10 +418,10 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     for (int q = 0; q < 3; ++q) { CREATE_TRY(dalloc(&c->bufA[q], (size_t)nt)); CREATE_TRY(dalloc(&c->bufB[q], (size_t)nt)); }
     c->cur = c->bufA; c->sav = c->bufA;
     CREATE_TRY(dalloc(&c->ceh, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->ceu, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->cev, (size_t)3 * nt));
-    CREATE_TRY(dalloc(&c->cgx, (size_t)nt)); CREATE_TRY(dalloc(&c->cgy, (size_t)nt)); CREATE_TRY(dalloc(&c->pw_list, (size_t)nt));
+    CREATE_TRY(dalloc(&c->cgx, (size_t)nt)); CREATE_TRY(dalloc(&c->cgy, (size_t)nt)); CREATE_TRY(dalloc(&c->pw_list, (size_t)nt)); CREATE_TRY(dalloc(&c->rs_list, (size_t)nt));
     CREATE_TRY(dalloc(&c->f0, (size_t)ne)); CREATE_TRY(dalloc(&c->f1, (size_t)ne)); CREATE_TRY(dalloc(&c->f2, (size_t)ne));
     CREATE_TRY(dalloc(&c->dti, (size_t)nt)); CREATE_TRY(dalloc(&c->cls, (size_t)nt));
-    CREATE_TRY(dalloc(&c->scal, 8)); CREATE_TRY(dalloc(&c->flags, 4));
+    CREATE_TRY(dalloc(&c->scal, 8)); CREATE_TRY(dalloc(&c->flags, 8));
     CREATE_TRY(dalloc(&c->diag, (size_t)6 * kDiagBlocks + 8));
     for (int q = 0; q < 3; ++q) {
         CREATE_TRY(cudaMemset(c->bufA[q], 0, sizeof(double) * nt));
@@ -433,7 +433,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(cudaMemset(c->f0, 0, sizeof(double) * ne)); CREATE_TRY(cudaMemset(c->f1, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->f2, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->dti, 0, sizeof(double) * nt)); CREATE_TRY(cudaMemset(c->cls, 0, nt));
-    CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 4));
+    CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 8));
     const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 0, 0, 0, 0};
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaDeviceSynchronize());
@@ -518,7 +518,10 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     int rc;
-    if (begin) CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, 2 * sizeof(int), c->stream));  // part-wet list counter
+    if (begin) {  // work-list counters: part-wet cells [1], generic-reconstruction cells [4]
+        CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, sizeof(int), c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
+    }
     if (last > first) {
         int kt = kt_begin(c, KT_RECONSTRUCT);
         // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
@@ -529,6 +532,13 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         if ((rc = launch_check(c, "k_reconstruct"))) return rc;
     }
     if (finish) {
+#if SWE_K1_SPLIT
+        int kts = kt_begin(c, KT_PARTWET2);  // accounted with the part-wet pass: both are O(front) list kernels
+        if (c->taps) k_reconstruct_slow<true><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
+        else k_reconstruct_slow<false><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
+        kt_end(c, kts);
+        if ((rc = launch_check(c, "k_reconstruct_slow"))) return rc;
+#endif
         int kt = kt_begin(c, KT_PARTWET2);
         if (c->taps) k_partwet2<true><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
         else k_partwet2<false><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);

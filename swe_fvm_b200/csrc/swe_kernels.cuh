@@ -44,9 +44,10 @@ struct DevFields {
     double *dti;                     // [nt] draining dt
     signed char *cls;                // [nt] 0 dry, 1 part-wet, 2 full-wet
     int *pw_list;                    // [nt] compacted ids of part-wet cells (pass 2 work list)
+    int *rs_list;                    // [nt] cells left to the generic reconstruction kernel (K1s)
     double *scal;                    // [0] min_len_to_wavespeed, [1] dt, [2] time, [3] running min
     int *flags;                      // [0] non-finite state seen, [1] part-wet count, [2] K1 tile counter,
-                                     // [3] flux block ticket
+                                     // [3] flux block ticket, [4] generic-reconstruction list count
 };
 
 constexpr int kBlock = 128;
@@ -76,20 +77,18 @@ template <bool TAPS>
 __device__ __forceinline__ void emit_edge(const DevFields &s, int slot, const Muscl &M, double cx, double cy,
                                           double mx, double my, double mb) {
     const double dx = mx - cx, dy = my - cy;
-    double a0 = M.o0 + (M.g00 * dx + M.g01 * dy);
-    double a1 = M.o1 + (M.g10 * dx + M.g11 * dy);
-    double a2 = M.o2 + (M.g20 * dx + M.g21 * dy);
-    if (!((a0 - mb) >= 0)) { a0 = mb; a1 = 0.; a2 = 0.; }
-    double h = a0 - mb;
-    double ew, eh, eu, ev;
+    const double a0 = M.o0 + (M.g00 * dx + M.g01 * dy);
+    double eu = M.o1 + (M.g10 * dx + M.g11 * dy);
+    double ev = M.o2 + (M.g20 * dx + M.g21 * dy);
+    // AtPoint's dry clamp (a0 - mb < 0 -> (mb,0,0)) followed by PrimAssigner's (h <= 1e-12 ->
+    // (mb,0,0)) collapse into one test: a clamped point has h = 0, which is not wet either.
+    const double h = a0 - mb;
+    double ew = a0, eh = h;
     if (!is_wet(h)) {
         ew = mb; eh = 0.; eu = 0.; ev = 0.;
-    } else {
-        ew = a0; eh = h; eu = a1; ev = a2;
-        if (h < 1e-3) {
-            double fac = sqrt(2.0) * h / sqrt(h * h + 1e-6);
-            eu *= fac; ev *= fac;
-        }
+    } else if (h < 1e-3) {
+        const double fac = sqrt(2.0) * h / sqrt(h * h + 1e-6);
+        eu *= fac; ev *= fac;
     }
     st_once(s.ceh + slot, eh); st_once(s.ceu + slot, eu); st_once(s.cev + slot, ev);
     if (TAPS) s.cew[slot] = ew;
@@ -99,17 +98,8 @@ __device__ __forceinline__ void emit_edge(const DevFields &s, int slot, const Mu
     // (g00, g01) is stored (once per cell) and the sum is formed where it is consumed.
 }
 
-__device__ __forceinline__ double muscl_w_at(const Muscl &M, double cx, double cy, double px, double py, double pz) {
-    double a0 = M.o0 + (M.g00 * (px - cx) + M.g01 * (py - cy));
-    if (!((a0 - pz) >= 0)) a0 = pz;
-    return a0;
-}
-
-// ---------------------------------------------------------------------------------------
-// K1: classification + pass-1 reconstruction of every cell (src/SpaceDisc.cpp:37-45,
-// src/MUSCLObject.cpp:13-112). Part-wet cells are appended to the pass-2 work list.
-// ---------------------------------------------------------------------------------------
-// K1 dispatch: persistent grid-stride, exactly one resident wave (3 CTAs/SM at ~160 registers).
+// K1 dispatch: persistent grid-stride, exactly one resident wave (4 CTAs/SM at 128 registers for the
+// fast path; the generic routine needs ~160).
 // Measured alternatives that were slower at 64M cells (profiles/README.md): one CTA per 128-cell
 // tile (3.78 vs 3.30 ms), in-order atomic tile dispatch (3.66), register caps that spill (5.2-5.9),
 // shared-memory parking of the neighbour states for 16-20 warps/SM (3.55-3.69), a cp.async (LDGSTS)
@@ -120,10 +110,10 @@ __device__ __forceinline__ double muscl_w_at(const Muscl &M, double cx, double c
 #endif
 constexpr int kK1Block = SWE_K1_BLOCK;
 #ifndef SWE_K1_MIN_BLOCKS
-#define SWE_K1_MIN_BLOCKS 3
+#define SWE_K1_MIN_BLOCKS 4
 #endif
 #ifndef SWE_K1_GRID_PER_SM
-#define SWE_K1_GRID_PER_SM 3
+#define SWE_K1_GRID_PER_SM 4
 #endif
 __device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32-byte read-only gather
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
@@ -241,6 +231,96 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
     emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mxk[2], myk[2], mbk[2]);
 }
 
+// K1 fast path: dry cells and full-wet cells whose three neighbours are all full-wet (the bulk of
+// any mesh). Without the part-wet patching logic the support points are the neighbour centroids and
+// the support values the neighbour means, which needs fewer registers and selects. Every other
+// cell (part-wet cells, full-wet cells next to a dry / part-wet one) is appended to rs_list and
+// reconstructed by the generic routine in k_reconstruct_slow — same formulas, same bits.
+#ifndef SWE_K1_SPLIT
+#define SWE_K1_SPLIT 1
+#endif
+template <bool TAPS>
+__device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const DevFields &s, const int i, const int ip0,
+                                                      const int ip1, const int ip2, const int it0, const int it1,
+                                                      const int it2) {
+    const int nt = m.nt;
+    const int j0 = max(it0, 0), j1 = max(it1, 0), j2 = max(it2, 0);
+    const double4 P0 = ldg4(m.node + ip0), P1 = ldg4(m.node + ip1), P2 = ldg4(m.node + ip2);
+    const double4 Gi = ldg4(m.cgeo + i);
+    const double w = __ldg(s.w + i), u = __ldg(s.u + i), v = __ldg(s.v + i);
+    const double N00 = __ldg(s.w + j0), N01 = __ldg(s.u + j0), N02 = __ldg(s.v + j0);
+    const double N10 = __ldg(s.w + j1), N11 = __ldg(s.u + j1), N12 = __ldg(s.v + j1);
+    const double N20 = __ldg(s.w + j2), N21 = __ldg(s.u + j2), N22 = __ldg(s.v + j2);
+    const double4 G0 = ldg4(m.cgeo + j0), G1 = ldg4(m.cgeo + j1), G2 = ldg4(m.cgeo + j2);
+    const double cx = Gi.x, cy = Gi.y, cb = Gi.z;
+    const bool bnd = (it0 | it1 | it2) < 0;
+    const bool dry = !is_wet(w - cb);
+    const bool full = !bnd && (smax(smax(P0.z, P1.z), P2.z) < w);
+    const bool nbfull = (G0.w < N00) && (G1.w < N10) && (G2.w < N20);
+    if (!dry && !(full && nbfull)) return false;
+    s.cls[i] = dry ? 0 : 2;
+
+    const double mx0 = 0.5 * (P0.x + P1.x), my0 = 0.5 * (P0.y + P1.y), mb0 = 0.5 * (P0.z + P1.z);
+    const double mx1 = 0.5 * (P1.x + P2.x), my1 = 0.5 * (P1.y + P2.y), mb1 = 0.5 * (P1.z + P2.z);
+    const double mx2 = 0.5 * (P2.x + P0.x), my2 = 0.5 * (P2.y + P0.y), mb2 = 0.5 * (P2.z + P0.z);
+    Muscl M;
+    M.g00 = M.g01 = M.g10 = M.g11 = M.g20 = M.g21 = 0.;
+    if (dry) {  // ReconstructDryCell (src/MUSCLObject.cpp:31-36)
+        M.o0 = cb; M.o1 = 0.; M.o2 = 0.;
+        gradient3(P0.x, P0.y, P0.z, P1.x, P1.y, P1.z, P2.x, P2.y, P2.z, M.g00, M.g01);
+    } else {  // ReconstructFullWetCell (:38-84) with three full-wet neighbours
+        M.o0 = w; M.o1 = u; M.o2 = v;
+        const Lu2 lu = lu2_factor(G0.x, G0.y, G1.x, G1.y, G2.x, G2.y);
+        double d00, d01, d10, d11, d20, d21;
+        lu2_solve(lu, N00, N10, N20, d00, d01);
+        const double md = 1. - 1. / 3., mo = 0. - 1. / 3.;
+        const double dx0 = (P0.x * md + P1.x * mo) + P2.x * mo, dy0 = (P0.y * md + P1.y * mo) + P2.y * mo;
+        const double dx1 = (P0.x * mo + P1.x * md) + P2.x * mo, dy1 = (P0.y * mo + P1.y * md) + P2.y * mo;
+        const double dx2 = (P0.x * mo + P1.x * mo) + P2.x * md, dy2 = (P0.y * mo + P1.y * mo) + P2.y * md;
+        const double hp0 = ((d00 * dx0 + d01 * dy0) + w) - P0.z;
+        const double hp1 = ((d00 * dx1 + d01 * dy1) + w) - P1.z;
+        const double hp2 = ((d00 * dx2 + d01 * dy2) + w) - P2.z;
+        const bool positive = is_wet(hp0) && is_wet(hp1) && is_wet(hp2);
+        lu2_solve(lu, N01, N11, N21, d10, d11);
+        lu2_solve(lu, N02, N12, N22, d20, d21);
+        if (!positive) { d00 = d01 = d10 = d11 = d20 = d21 = 0.; }
+        // on/off TVD limiter (:74-81): lo <= v_e <= hi with lo/hi = min/max of the two cell means
+        const double ex0 = mx0 - cx, ey0 = my0 - cy, ex1 = mx1 - cx, ey1 = my1 - cy, ex2 = mx2 - cx, ey2 = my2 - cy;
+        double t0 = 1., t1 = 1., t2 = 1.;
+#define SWE_TVD(T, OWN, NB, DA, DB, EX, EY)                                             \
+        {                                                                               \
+            const double vek = (OWN) + ((DA) * (EX) + (DB) * (EY));                     \
+            /* min(own,nb) <= vek <= max(own,nb) without forming min / max */           \
+            const bool inb = ((OWN) <= (NB)) ? (((OWN) <= vek) && (vek <= (NB)))        \
+                                             : (((NB) <= vek) && (vek <= (OWN)));       \
+            if (!inb) T = 0.;                                                           \
+        }
+        SWE_TVD(t0, w, N00, d00, d01, ex0, ey0) SWE_TVD(t1, u, N01, d10, d11, ex0, ey0) SWE_TVD(t2, v, N02, d20, d21, ex0, ey0)
+        SWE_TVD(t0, w, N10, d00, d01, ex1, ey1) SWE_TVD(t1, u, N11, d10, d11, ex1, ey1) SWE_TVD(t2, v, N12, d20, d21, ex1, ey1)
+        SWE_TVD(t0, w, N20, d00, d01, ex2, ey2) SWE_TVD(t1, u, N21, d10, d11, ex2, ey2) SWE_TVD(t2, v, N22, d20, d21, ex2, ey2)
+#undef SWE_TVD
+        M.g00 = t0 * d00; M.g01 = t0 * d01;
+        M.g10 = t1 * d10; M.g11 = t1 * d11;
+        M.g20 = t2 * d20; M.g21 = t2 * d21;
+    }
+    st_once(s.cgx + i, M.g00); st_once(s.cgy + i, M.g01);
+    emit_edge<TAPS>(s, i, M, cx, cy, mx0, my0, mb0);
+    emit_edge<TAPS>(s, nt + i, M, cx, cy, mx1, my1, mb1);
+    emit_edge<TAPS>(s, 2 * nt + i, M, cx, cy, mx2, my2, mb2);
+    return true;
+}
+
+// generic reconstruction of the cells the fast path skipped (compacted list, O(front length))
+template <bool TAPS>
+__global__ void __launch_bounds__(kBlock) k_reconstruct_slow(DevMesh m, DevFields s) {
+    const int nt = m.nt;
+    const int n = min(s.flags[4], nt);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int i = s.rs_list[q];
+        reconstruct_cell<TAPS>(m, s, i, m.tp[i], m.tp[nt + i], m.tp[2 * nt + i], m.tt[i], m.tt[nt + i], m.tt[2 * nt + i]);
+    }
+}
+
 // persistent grid-stride kernel over the cell range [first, last); the ids of the thread's next
 // cell are fetched before the current cell is processed (hides the first memory round trip)
 template <bool TAPS>
@@ -258,7 +338,11 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(Dev
             np0 = __ldg(m.tp + nx); np1 = __ldg(m.tp + nt + nx); np2 = __ldg(m.tp + 2 * nt + nx);
             nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
         }
+#if SWE_K1_SPLIT
+        if (!reconstruct_cell_fast<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
+#else
         reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
+#endif
         if (nx >= last) break;
         i = nx; ip0 = np0; ip1 = np1; ip2 = np2; it0 = nt0; it1 = nt1; it2 = nt2;
     }
