@@ -46,8 +46,8 @@ KERNEL_BYTES_PER_CELL = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# profiles/r1_v2_ncu_full_summary.csv (64M-cell fully-wet workload); None for other workloads
-NCU_TRAFFIC_BYTES_64M = {"k_reconstruct": 13.320e9, "k_flux": 11.539e9, "k_drain": 3.749e9, "k_update": 13.953e9}
+# profiles/r1_v3_ncu_full_summary.csv (64M-cell fully-wet workload); None for other workloads
+NCU_TRAFFIC_BYTES_64M = {"k_reconstruct": 12.752e9, "k_flux": 10.571e9, "k_drain": 3.751e9, "k_update": 13.980e9}
 
 
 def peaks():
@@ -368,7 +368,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (NCU_TRAFFIC_BYTES_64M.get(dom) if (args.n == 4096 and args.case == "fully_wet") else None),
-                     "traffic_source": "ncu --set full, profiles/r1_v2_ncu_full_summary.csv", "peak_source": peak_src,
+                     "traffic_source": "ncu --set full, profiles/r1_v3_ncu_full_summary.csv", "peak_source": peak_src,
                      "alg_bytes_per_launch": dom_bytes,
                      "step": {"alg_bytes_per_cell_update": B_PER_CELL_UPDATE_SSPRK2, "achieved": step_gbps,
                               "frac": step_gbps / peak, "per": "GPU"},
