@@ -157,3 +157,30 @@ def test_device_side_cases_match_host():
             np.sqrt((A * (h * q[:, 2] - ex[:, 1] * ex[:, 3]) ** 2).sum())]
     assert np.allclose(err, want, rtol=1e-9, atol=1e-14)
     assert err[0] < 1e-2
+
+
+def test_config3_full_size_bit_parity():
+    """The bench workload itself (67 108 864 cells, fully-wet variant, Hilbert numbering on the
+    device): two SSPRK2 HLLC<Einfeldt> steps with dt = CFLdt on the GPU equal the (OpenMP) CPU oracle
+    bit for bit, including the CFL time step."""
+    from swe_fvm_b200 import Case, StructTriangMesh
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    from oracle.oracle import Oracle
+    n = 4096
+    mesh = StructTriangMesh(n, n, 4.0 / n)
+    case = Case("fully_wet", 2.0, 2.0, 4.0)
+    case.set_bathymetry(mesh)
+    v0 = case.initial_state(mesh, quad_n=1)
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0, reorder=True)
+    td = TimeDisc(sd)
+    ref = Oracle(mesh, threads=0)
+    ref.set_state(v0)
+    dt = 1e-5
+    for _ in range(2):
+        Solvers.SSPRK2(td, dt)
+        ref.step(1, 1, 2, dt)
+        dt = td.CFLdt()
+        assert dt == ref.cfl_dt()
+    got, want = sd.GetVolField(), ref.get_state()
+    assert rel_l2(got, want) <= 1e-12
+    np.testing.assert_array_equal(got, want)
