@@ -243,7 +243,7 @@ def run_gpu(args):
     SSPRK2 = 1
     if dec is not None:
         local = swd.GpuLocal(sd, has_classes=True)
-        solver = swd.DistributedSolver(dec, local, overlap=not args.no_overlap)
+        solver = swd.DistributedSolver(dec, local, overlap=not args.no_overlap, transport=args.halo)
 
         def run_steps(k):
             solver.run(SSPRK2, k, None, dt0=dt_first[0])
@@ -356,7 +356,7 @@ def run_gpu(args):
         "config": {"workload": workload_name(args, world), "wet_cell_fraction": wet_frac,
                    "cells_per_gpu": int(n_owned), "cells_total": int(cells_total),
                    "l2": "inputs larger than L2 (state + edge fields >> 126 MB), no flush needed",
-                   "parallelism": "1 GPU" if world == 1 else (f"{world} strips, 3-row halo, NCCL send/recv "
+                   "parallelism": "1 GPU" if world == 1 else (f"{world} strips, 3-row halo, {'peer-memory stores over NVLink (CUDA IPC)' if solver.halo.transport == 'p2p' else 'NCCL send/recv'} "
                                    f"{'overlapped with interior reconstruction' if solver.overlap else '(not overlapped)'} + min all-reduce"),
                    "dt": "CFLdt of the previous step (device resident)", "setup_s": t_setup,
                    "device_numbering": "hilbert" if args.reorder else "caller"},
@@ -397,6 +397,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange with interior work")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1 halo transport: p2p = pack kernel stores into the peer GPU's buffer over NVLink "
+                         "(CUDA IPC) + flag; nccl = pack, NCCL send/recv, unpack")
     ap.add_argument("--no-reorder", dest="reorder", action="store_false",
                     help="keep the caller's numbering on the device (default: Hilbert-curve renumbering of cells / "
                          "edges / nodes, A/B-measured +3.8 %% on this workload)")

@@ -189,6 +189,21 @@ SWE_API int swe_halo_set_lists(swe_ctx *ctx, int64_t nsend, const int64_t *send_
  * (NCCL or peer-mapped buffers). */
 SWE_API int swe_halo_pack(swe_ctx *ctx, double *dev_sendbuf);
 SWE_API int swe_halo_unpack(swe_ctx *ctx, const double *dev_recvbuf);
+/* Peer-memory halo transport: the pack kernel stores this rank's boundary states straight into the
+ * neighbour GPU's receive buffer over NVLink (CUDA IPC mapping) and publishes the exchange number
+ * in the neighbour's flag slot; the receiver waits on its flags (with a time-out) and unpacks. No
+ * NCCL call on the data path. Set-up: swe_halo_set_lists, then swe_halo_p2p_alloc (returns three
+ * 64-byte IPC handles: receive buffer 0, receive buffer 1, flags), exchange of the handles and of
+ * the segment offsets by the host layer, one swe_halo_p2p_connect per peer. Per exchange:
+ * swe_halo_p2p_push then swe_halo_p2p_pull (both asynchronous on the ctx stream). The flag slot
+ * of peer k is k (its position in this rank's peer list). */
+SWE_API int swe_halo_p2p_alloc(swe_ctx *ctx, int32_t npeers, unsigned char *handles_3x64);
+SWE_API int swe_halo_p2p_connect(swe_ctx *ctx, int64_t send_start, int64_t send_count,
+                                 const unsigned char *peer_handles_3x64, int64_t dst_offset_cells,
+                                 int32_t my_slot_in_peer_flags);
+SWE_API int swe_halo_p2p_push(swe_ctx *ctx);
+SWE_API int swe_halo_p2p_pull(swe_ctx *ctx);
+SWE_API int swe_halo_p2p_error(swe_ctx *ctx); /* 1 if a wait timed out */
 /* replace the running min_len_to_wavespeed (after the global min all-reduce). */
 SWE_API int swe_set_min_len_to_wavespeed(swe_ctx *ctx, double v);
 /* device address of the fp64 scalar holding min_len_to_wavespeed (for in-place NCCL all-reduce). */

@@ -104,6 +104,11 @@ SYMBOLS = {
     "swe_halo_set_lists": (C.c_int, [_P, C.c_int64, _I64, C.c_int64, _I64]),
     "swe_halo_pack": (C.c_int, [_P, _P]),
     "swe_halo_unpack": (C.c_int, [_P, _P]),
+    "swe_halo_p2p_alloc": (C.c_int, [_P, C.c_int32, _U8]),
+    "swe_halo_p2p_connect": (C.c_int, [_P, C.c_int64, C.c_int64, _U8, C.c_int64, C.c_int32]),
+    "swe_halo_p2p_push": (C.c_int, [_P]),
+    "swe_halo_p2p_pull": (C.c_int, [_P]),
+    "swe_halo_p2p_error": (C.c_int, [_P]),
     "swe_set_min_len_to_wavespeed": (C.c_int, [_P, C.c_double]),
     "swe_min_len_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "swe_hostmesh_struct": (C.c_int, [C.POINTER(_P), C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64]),

@@ -40,6 +40,7 @@ struct swe_ctx {
     double *area = nullptr, *cb = nullptr, *elen = nullptr, *dmin = nullptr;
     int *n2c_start = nullptr, *n2c_cells = nullptr;
     unsigned char *cfl_mask = nullptr;
+    double *dmin0 = nullptr;  // unmasked copy of dmin (only once a CFL edge mask was set)
     int *cell_old = nullptr, *edge_old = nullptr, *node_old = nullptr;  // device id -> caller id
     std::vector<int> cell_new;  // caller id -> device id (host; halo lists)
     // fields
@@ -58,6 +59,13 @@ struct swe_ctx {
     int *send_cells = nullptr, *recv_cells = nullptr;
     int nsend = 0, nrecv = 0;
     bool saved_pending = false;
+    // peer-memory halo transport (swe_halo_p2p_*)
+    struct P2PPeer { int send_start, send_count; double *peer_recv[2]; int *peer_flag; };
+    std::vector<P2PPeer> p2p_peers;
+    double *p2p_recv[2] = {nullptr, nullptr};  // local receive buffers (parity of the exchange number)
+    int *p2p_flags = nullptr;                  // [npeers] sequence numbers written by the peers, [npeers] = error
+    int p2p_seq = 0;
+    std::vector<void *> p2p_imported;
     // optional per-kernel CUDA-event timing (bench.py roofline): pairs recorded on c->stream
     bool ktiming = false;
     struct KtPair { cudaEvent_t a, b; int id; };
@@ -184,11 +192,15 @@ static void destroy_ctx(swe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     void *ptrs[] = {c->tt, c->te, c->tp, c->slotL, c->slotR, c->cgeo, c->node, c->en, c->area, c->cb, c->elen, c->dmin,
-                    c->n2c_start, c->n2c_cells, c->cfl_mask, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
+                    c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
                     c->send_cells, c->recv_cells};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
+    if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
+    if (c->p2p_recv[1]) cudaFree(c->p2p_recv[1]);
+    if (c->p2p_flags) cudaFree(c->p2p_flags);
     for (auto &p : c->kt_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto &p : c->kt_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete c;
@@ -849,9 +861,8 @@ SWE_API int swe_case_l2_error(swe_ctx *c, const swe_case *cs, double t, double o
 SWE_API int swe_set_cfl_edge_mask(swe_ctx *c, const uint8_t *mask) {
     if (!c) return SWE_ERR_INVALID;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    if (!mask) {
-        if (c->cfl_mask) cudaFree(c->cfl_mask);
-        c->cfl_mask = nullptr;
+    if (!mask) {  // back to "all edges count"
+        if (c->dmin0) CUDA_TRY(c, cudaMemcpyAsync(c->dmin, c->dmin0, sizeof(double) * c->ne, cudaMemcpyDeviceToDevice, c->stream));
         return SWE_OK;
     }
     std::vector<unsigned char> h((size_t)c->ne);
@@ -864,7 +875,12 @@ SWE_API int swe_set_cfl_edge_mask(swe_ctx *c, const uint8_t *mask) {
     }
     if (!c->cfl_mask) CUDA_TRY(c, dalloc(&c->cfl_mask, (size_t)c->ne));
     CUDA_TRY(c, cudaMemcpy(c->cfl_mask, h.data(), (size_t)c->ne, cudaMemcpyHostToDevice));
-    return SWE_OK;
+    if (!c->dmin0) {
+        CUDA_TRY(c, dalloc(&c->dmin0, (size_t)c->ne));
+        CUDA_TRY(c, cudaMemcpy(c->dmin0, c->dmin, sizeof(double) * c->ne, cudaMemcpyDeviceToDevice));
+    }
+    k_apply_cfl_mask<<<nblk(c->ne, 256), 256, 0, c->stream>>>(c->ne, c->cfl_mask, c->dmin0, c->dmin);
+    return launch_check(c, "k_apply_cfl_mask");
 }
 
 SWE_API int swe_halo_set_lists(swe_ctx *c, int64_t nsend, const int64_t *send_cells, int64_t nrecv, const int64_t *recv_cells) {
@@ -901,6 +917,96 @@ SWE_API int swe_halo_unpack(swe_ctx *c, const double *buf) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     k_halo_unpack<<<nblk(c->nrecv, 256), 256, 0, c->stream>>>(c->nrecv, c->recv_cells, buf, c->cur[0], c->cur[1], c->cur[2]);
     return launch_check(c, "k_halo_unpack");
+}
+
+
+// ---- peer-memory halo transport (CUDA IPC + NVLink stores) ----
+// 1. swe_halo_p2p_alloc: allocates this rank's two receive buffers (3*nrecv doubles each, selected by the
+//    parity of the exchange number) and npeers flag slots; returns their IPC handles (64 bytes each).
+// 2. the host layer exchanges handles / segment offsets between ranks (any transport) and calls
+//    swe_halo_p2p_connect once per peer.
+// 3. per exchange: swe_halo_p2p_push (pack kernels storing into the peers' buffers + flags) and
+//    swe_halo_p2p_pull (wait for the peers' flags, unpack).
+SWE_API int swe_halo_p2p_alloc(swe_ctx *c, int32_t npeers, unsigned char *handles_3x64) {
+    if (!c || npeers <= 0 || npeers > 32 || !handles_3x64 || c->nrecv <= 0) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->p2p_flags) { c->err = "swe_halo_p2p_alloc: already allocated"; return SWE_ERR_INVALID; }
+    for (int q = 0; q < 2; ++q) {
+        CUDA_TRY(c, cudaMalloc((void **)&c->p2p_recv[q], sizeof(double) * 3 * (size_t)c->nrecv));
+        CUDA_TRY(c, cudaMemset(c->p2p_recv[q], 0, sizeof(double) * 3 * (size_t)c->nrecv));
+    }
+    CUDA_TRY(c, cudaMalloc((void **)&c->p2p_flags, sizeof(int) * 64));
+    CUDA_TRY(c, cudaMemset(c->p2p_flags, 0, sizeof(int) * 64));
+    cudaIpcMemHandle_t h;
+    void *ptrs[3] = {c->p2p_recv[0], c->p2p_recv[1], c->p2p_flags};
+    for (int q = 0; q < 3; ++q) {
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h, ptrs[q]));
+        std::memcpy(handles_3x64 + 64 * q, &h, 64);
+    }
+    c->p2p_peers.clear();
+    c->p2p_seq = 0;
+    CUDA_TRY(c, cudaDeviceSynchronize());
+    return SWE_OK;
+}
+// peer: send_start/send_count = this rank's segment of the send list for that peer; handles = the peer's three
+// handles; dst_offset = where (in cells) this rank's segment starts in the peer's receive buffers;
+// my_slot = index of this rank in the peer's flag array.
+SWE_API int swe_halo_p2p_connect(swe_ctx *c, int64_t send_start, int64_t send_count, const unsigned char *peer_handles_3x64,
+                                 int64_t dst_offset, int32_t my_slot) {
+    if (!c || !peer_handles_3x64 || send_start < 0 || send_count < 0 || send_start + send_count > c->nsend || my_slot < 0 || my_slot >= 32)
+        return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    void *mapped[3];
+    for (int q = 0; q < 3; ++q) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, peer_handles_3x64 + 64 * q, 64);
+        CUDA_TRY(c, cudaIpcOpenMemHandle(&mapped[q], h, cudaIpcMemLazyEnablePeerAccess));
+        c->p2p_imported.push_back(mapped[q]);
+    }
+    swe_ctx::P2PPeer p;
+    p.send_start = (int)send_start; p.send_count = (int)send_count;
+    p.peer_recv[0] = (double *)mapped[0] + 3 * dst_offset;
+    p.peer_recv[1] = (double *)mapped[1] + 3 * dst_offset;
+    p.peer_flag = (int *)mapped[2] + my_slot;
+    c->p2p_peers.push_back(p);
+    return SWE_OK;
+}
+SWE_API int swe_halo_p2p_push(swe_ctx *c) {
+    if (!c || !c->p2p_flags) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int seq = ++c->p2p_seq;
+    int rc;
+    for (auto &p : c->p2p_peers) {
+        if (p.send_count > 0) {
+            k_halo_pack<<<nblk(p.send_count, 256), 256, 0, c->stream>>>(p.send_count, c->send_cells + p.send_start, c->cur[0],
+                                                                       c->cur[1], c->cur[2], p.peer_recv[seq & 1]);
+            if ((rc = launch_check(c, "k_halo_pack(peer)"))) return rc;
+        }
+        k_halo_signal<<<1, 1, 0, c->stream>>>(p.peer_flag, seq);
+        if ((rc = launch_check(c, "k_halo_signal"))) return rc;
+    }
+    return SWE_OK;
+}
+SWE_API int swe_halo_p2p_pull(swe_ctx *c) {
+    if (!c || !c->p2p_flags || c->p2p_seq <= 0) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int seq = c->p2p_seq;
+    int rc;
+    k_halo_wait<<<1, 32, 0, c->stream>>>(c->p2p_flags, (int)c->p2p_peers.size(), seq, 20000000000ll, c->flags + 5);
+    if ((rc = launch_check(c, "k_halo_wait"))) return rc;
+    if (c->nrecv > 0) {
+        k_halo_unpack<<<nblk(c->nrecv, 256), 256, 0, c->stream>>>(c->nrecv, c->recv_cells, c->p2p_recv[seq & 1], c->cur[0], c->cur[1], c->cur[2]);
+        if ((rc = launch_check(c, "k_halo_unpack"))) return rc;
+    }
+    return SWE_OK;
+}
+// 1 if a peer-memory wait timed out since the context was created
+SWE_API int swe_halo_p2p_error(swe_ctx *c) {
+    if (!c) return SWE_ERR_INVALID;
+    int flag = 0;
+    cudaSetDevice(c->device);
+    cudaMemcpy(&flag, c->flags + 5, sizeof(int), cudaMemcpyDeviceToHost);
+    return flag;
 }
 
 }  // extern "C"

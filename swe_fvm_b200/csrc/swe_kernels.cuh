@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
                 double cand = 1.0;
                 riemann_flux<FLUX, WS>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
                                        __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand);
-                if (m.cfl_mask == nullptr || m.cfl_mask[e]) l2w = (cand < l2w) ? cand : l2w;
+                l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
             }
             st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
             if (nx >= ne) break;
@@ -754,6 +754,33 @@ __global__ void k_halo_unpack(int n, const int *cells, const double *buf, double
     if (k >= n) return;
     const int c = cells[k];
     w[c] = buf[3 * (size_t)k]; u[c] = buf[3 * (size_t)k + 1]; v[c] = buf[3 * (size_t)k + 2];
+}
+
+// peer-memory halo transport: after the pack kernel stored this rank's boundary states straight into
+// the neighbour GPU's receive buffer (NVLink stores through a CUDA-IPC mapping), one thread publishes
+// the exchange sequence number in the neighbour's flag slot; the receiver spins on its own flags.
+// CFL edge mask (multi-GPU: only edges touching owned cells count): excluded edges get dmin = +inf,
+// so their length/wavespeed candidate is +inf and never wins the min — no mask test in the flux kernel
+__global__ void k_apply_cfl_mask(int ne, const unsigned char *mask, const double *dmin0, double *dmin) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    dmin[e] = mask[e] ? dmin0[e] : __longlong_as_double(0x7ff0000000000000ll);
+}
+__global__ void k_halo_signal(volatile int *peer_flag, int seq) {
+    __threadfence_system();
+    *peer_flag = seq;
+    __threadfence_system();
+}
+// waits until every peer has published `seq` (or ~timeout_cycles passed: sets err[0] = 1 instead of hanging)
+__global__ void k_halo_wait(volatile int *flags, int npeers, int seq, long long timeout_cycles, int *err) {
+    const int p = threadIdx.x;
+    if (p >= npeers) return;
+    const long long t0 = clock64();
+    while (flags[p] < seq) {
+        if (clock64() - t0 > timeout_cycles) { err[0] = 1; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------

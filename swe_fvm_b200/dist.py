@@ -148,16 +148,48 @@ class HaloExchanger:
     """Packs owned boundary cells, exchanges with every peer, unpacks into the halo cells.
     `local` supplies pack/unpack and a buffer allocator; tensors may be CPU (gloo) or CUDA (NCCL)."""
 
-    def __init__(self, dec: Decomposition, local):
+    def __init__(self, dec: Decomposition, local, transport: str = "nccl"):
         self.dec, self.local = dec, local
         self.nsend = sum(len(p[1]) for p in dec.peers)
         self.nrecv = sum(len(p[2]) for p in dec.peers)
-        self.sendbuf = local.alloc(3 * max(self.nsend, 1))
-        self.recvbuf = local.alloc(3 * max(self.nrecv, 1))
         local.set_halo_lists(dec.send_list(), dec.recv_list())
         self.bytes_per_exchange = 8 * 3 * (self.nsend + self.nrecv)
+        self.transport = transport if (dec.peers and getattr(local, "supports_p2p", False)) else "nccl"
+        if transport == "p2p" and self.transport != "p2p" and dec.peers:
+            raise ValueError("peer-memory halo transport needs a GPU local solver")
+        if self.transport == "p2p":
+            self._setup_p2p()
+        else:
+            self.sendbuf = local.alloc(3 * max(self.nsend, 1))
+            self.recvbuf = local.alloc(3 * max(self.nrecv, 1))
+
+    def _setup_p2p(self):
+        """Peer-memory transport: every rank allocates its receive buffers + flags, publishes their
+        CUDA-IPC handles and its receive-segment table; every sender maps the peer's buffers and
+        learns where its segment goes. Data then moves by NVLink stores from the pack kernel."""
+        import torch.distributed as dist
+        dec, L = self.dec, self.local
+        handles = L.p2p_alloc(len(dec.peers))
+        table, ro = {}, 0
+        for slot, (peer, s, r) in enumerate(dec.peers):
+            table[int(peer)] = (ro, len(r), slot)
+            ro += len(r)
+        gathered = [None] * dec.world
+        dist.all_gather_object(gathered, {"handles": handles, "table": table})
+        so = 0
+        for peer, s, r in dec.peers:
+            off, cnt, slot = gathered[peer]["table"][dec.rank]
+            if cnt != len(s):
+                raise RuntimeError("halo lists of neighbouring ranks disagree")
+            L.p2p_connect(so, len(s), gathered[peer]["handles"], off, slot)
+            so += len(s)
+        dist.barrier()
 
     def _post(self):
+        if self.transport == "p2p":
+            self.local.p2p_push()   # pack kernels store into the peers' buffers, then publish a flag
+            self.local.p2p_pull()   # wait for the peers' flags, unpack
+            return
         import torch.distributed as dist
         self.local.pack(self.sendbuf)
         ops, so, ro = [], 0, 0
@@ -204,9 +236,9 @@ class DistributedSolver:
         2: [(0.0, 1.0, 1.0), (0.75, 0.25, 0.25), (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0)],
     }
 
-    def __init__(self, dec: Decomposition, local, overlap: bool | None = None):
+    def __init__(self, dec: Decomposition, local, overlap: bool | None = None, transport: str = "nccl"):
         self.dec, self.local = dec, local
-        self.halo = HaloExchanger(dec, local)
+        self.halo = HaloExchanger(dec, local, transport)
         local.set_cfl_edge_mask(dec.cfl_edge_mask())
         self.exchanges = 0
         self.allreduces = 0
@@ -234,7 +266,17 @@ class DistributedSolver:
             self._interface_values()
             L.compute_fluxes()
             if k == len(stages) - 1 and self.dec.world > 1:
-                dist.all_reduce(L.min_len_tensor(), op=dist.ReduceOp.MIN)
+                # global CFL min: only the NEXT step's dt needs it, so on the GPU it runs on the side
+                # stream while this stage's draining-dt / update kernels execute
+                if getattr(L, "supports_overlap", False):
+                    L.begin_side_stream()
+                    try:
+                        dist.all_reduce(L.min_len_tensor(), op=dist.ReduceOp.MIN)
+                    finally:
+                        L.end_side_stream(allreduce=True)
+                    self._ar_pending = True
+                else:
+                    dist.all_reduce(L.min_len_tensor(), op=dist.ReduceOp.MIN)
                 self.allreduces += 1
             if k == 0 and len(stages) > 1:
                 L.save_state()
@@ -245,6 +287,9 @@ class DistributedSolver:
             else:
                 self.halo.exchange()
             self.exchanges += 1
+        if getattr(self, "_ar_pending", False):
+            L.wait_side_stream(allreduce=True)
+            self._ar_pending = False
         L.advance_dt(dt)
 
     def finish(self):
@@ -265,6 +310,28 @@ class GpuLocal:
     """The device context of this rank, driven through the per-stage C-ABI entry points."""
 
     supports_overlap = True
+    supports_p2p = True
+
+    def p2p_alloc(self, npeers: int) -> bytes:
+        import ctypes as C
+        buf = (C.c_uint8 * 192)()
+        self.sd._call("swe_halo_p2p_alloc", int(npeers), buf)
+        return bytes(buf)
+
+    def p2p_connect(self, send_start, send_count, peer_handles: bytes, dst_offset, my_slot):
+        import ctypes as C
+        buf = (C.c_uint8 * 192).from_buffer_copy(peer_handles)
+        self.sd._call("swe_halo_p2p_connect", int(send_start), int(send_count), buf, int(dst_offset), int(my_slot))
+
+    def p2p_push(self):
+        self.sd._call("swe_halo_p2p_push")
+
+    def p2p_pull(self):
+        self.sd._call("swe_halo_p2p_pull")
+
+    def p2p_error(self) -> bool:
+        from . import capi
+        return capi.lib().swe_halo_p2p_error(self.sd._ctx) == 1
 
     def __init__(self, sd, has_classes: bool = False):
         import torch
@@ -277,6 +344,7 @@ class GpuLocal:
         self._side = None
         self._ev_main = torch.cuda.Event()
         self._ev_side = torch.cuda.Event()
+        self._ev_ar = torch.cuda.Event()
         self._ctx_mgr = None
         sd.set_stream(self._main.cuda_stream)
 
@@ -290,14 +358,14 @@ class GpuLocal:
         self._ctx_mgr.__enter__()
         self.sd.set_stream(self._side.cuda_stream)
 
-    def end_side_stream(self):
-        self._ev_side.record(self._side)
+    def end_side_stream(self, allreduce: bool = False):
+        (self._ev_ar if allreduce else self._ev_side).record(self._side)
         self.sd.set_stream(self._main.cuda_stream)
         self._ctx_mgr.__exit__(None, None, None)
         self._ctx_mgr = None
 
-    def wait_side_stream(self):
-        self._main.wait_event(self._ev_side)
+    def wait_side_stream(self, allreduce: bool = False):
+        self._main.wait_event(self._ev_ar if allreduce else self._ev_side)
 
     def compute_interface_values_class(self, cls, begin, finish):
         self.sd._call("swe_compute_interface_values_class", int(cls), int(begin), int(finish))

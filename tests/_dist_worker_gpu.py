@@ -40,9 +40,12 @@ def main():
                    cell_class=dec.cell_classes())
     sd.set_stream(torch.cuda.current_stream().cuda_stream)
     local = swd.GpuLocal(sd, has_classes=True)
-    solver = swd.DistributedSolver(dec, local)
+    transport = os.environ.get("SWE_HALO", "nccl")
+    solver = swd.DistributedSolver(dec, local, transport=transport)
+    assert solver.halo.transport == transport
     solver.run(scheme, nsteps, None if adaptive else 2e-3, dt0=1e-3)
     sd.synchronize()
+    assert not local.p2p_error()
     st = sd.GetVolField()
     np.savez(f"{out}.{rank}.npz", gids=gids[dec.owned], state=st[dec.owned], minlen=float(local.min_len_tensor().item()))
     dist.barrier()

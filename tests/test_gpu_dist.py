@@ -133,8 +133,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
 @pytest.mark.parametrize("mode", ["strips", "general"])
-def test_nccl_two_gpus_bitwise(tmp_path, mode):
+def test_nccl_two_gpus_bitwise(tmp_path, mode, transport):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -142,7 +143,7 @@ def test_nccl_two_gpus_bitwise(tmp_path, mode):
     out = str(tmp_path / "res")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_dist_worker_gpu.py"), mode, out, "30", "1", "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, SWE_HALO=transport))
     assert r.returncode == 0, r.stderr[-3000:]
     if mode == "strips":
         mesh, case, v0 = make_case("classic_thacker", 64, quad_n=4)
