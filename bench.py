@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--case", default="fully_wet", choices=["fully_wet", "thacker"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-n", type=int, default=1024)
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange with interior work")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],

@@ -111,7 +111,6 @@ static DevMesh dev_mesh(const swe_ctx *c) {
     m.cgeo = c->cgeo; m.area = c->area; m.cb = c->cb; m.node = c->node;
     m.n2c_start = c->n2c_start; m.n2c_cells = c->n2c_cells;
     m.slotL = c->slotL; m.slotR = c->slotR; m.en = c->en; m.elen = c->elen; m.dmin = c->dmin;
-    m.cfl_mask = c->cfl_mask;
     return m;
 }
 static DevFields dev_fields(const swe_ctx *c) {

@@ -1,5 +1,6 @@
-// swe_kernels.cuh — the hot path: one RK stage = reconstruct -> (part-wet pass 2) -> edge flux
-// + CFL min -> draining dt -> stage update. Hand-written fp64 CUDA for sm_100a.
+// swe_kernels.cuh — the hot path: one RK stage = reconstruct (fast kernel + two list-driven passes
+// for the wet/dry front) -> edge flux + CFL min -> draining dt -> stage update. Hand-written fp64
+// CUDA for sm_100a; no tensor cores (nothing here is a dense contraction).
 //
 // Data layout in HBM (structure of arrays, int32 ids, device numbering):
 //   cells : tt/te/tp[k*nt+i] (k-major so a warp reads 32 consecutive ids), cgeo[i] = 32-byte
@@ -30,8 +31,7 @@ struct DevMesh {
     const int *n2c_start, *n2c_cells;  // node -> incident cells (CSR), pass 2 and taps only
     const int *slotL, *slotR;
     const double2 *en;
-    const double *elen, *dmin;
-    const unsigned char *cfl_mask;  // nullable
+    const double *elen, *dmin;  // dmin = +inf on edges excluded from the CFL min (multi-GPU halo edges)
 };
 
 struct DevFields {
@@ -46,8 +46,8 @@ struct DevFields {
     int *pw_list;                    // [nt] compacted ids of part-wet cells (pass 2 work list)
     int *rs_list;                    // [nt] cells left to the generic reconstruction kernel (K1s)
     double *scal;                    // [0] min_len_to_wavespeed, [1] dt, [2] time, [3] running min
-    int *flags;                      // [0] non-finite state seen, [1] part-wet count, [2] K1 tile counter,
-                                     // [3] flux block ticket, [4] generic-reconstruction list count
+    int *flags;                      // [0] non-finite state seen, [1] part-wet list count, [3] flux block ticket,
+                                     // [4] generic-reconstruction list count, [5] peer-memory wait timed out
 };
 
 constexpr int kBlock = 128;

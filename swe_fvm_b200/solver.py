@@ -132,6 +132,18 @@ class SpaceDisc:
         self._call("swe_get_time", C.byref(v))
         return v.value
 
+    # -- checkpoint / restart (binary; the reference only has text dumps, examples/Main.cpp:65-73) --
+    def save_checkpoint(self, path: str):
+        np.savez(path, state=self.GetVolField(), time=self.time(), nt=self.nt, cor=self.cor)
+
+    def load_checkpoint(self, path: str) -> float:
+        """Restores the state; returns the simulated time stored with it."""
+        with np.load(path) as z:
+            if int(z["nt"]) != self.nt:
+                raise ValueError("checkpoint belongs to a different mesh")
+            self.SetVolField(z["state"])
+            return float(z["time"])
+
     def kernel_timing(self, enable: bool = True):
         self._call("swe_kernel_timing", int(enable))
 

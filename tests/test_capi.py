@@ -76,3 +76,16 @@ def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
         for f in files:
             assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/swe_b200.h must be consumable from C (the boundary is a C ABI, not a C++ one)."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "swe_b200.h"\n'
+                   'int main(void) { swe_mesh m; swe_case c; swe_ctx *ctx = 0; (void)m; (void)c; (void)ctx;\n'
+                   '  return (int)(SWE_OK + SWE_SSPRK2 - SWE_SSPRK2 + SWE_HLLC - SWE_HLLC); }\n')
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

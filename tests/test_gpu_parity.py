@@ -139,3 +139,19 @@ def test_mass_conservation_and_diagnostics(cases):
     for k, key in enumerate(["mass", "kinetic", "potential"]):
         assert abs(d[key] - o[k]) <= 1e-12 * max(abs(o[k]), 1e-30)
     assert d["vmax"] == o[3] and d["hmin"] == o[4]
+
+
+def test_checkpoint_restart_is_exact(cases, tmp_path):
+    from swe_fvm_b200.solver import Solvers
+    mesh, case, v0 = cases["thacker64"]
+    sd, td, ref = _pair(mesh, v0, taps=False)
+    Solvers.run(td, "ssprk2", 40, dt=2e-3)
+    straight = sd.GetVolField()
+    sd.SetVolField(v0)
+    Solvers.run(td, "ssprk2", 15, dt=2e-3)
+    sd.save_checkpoint(str(tmp_path / "ck.npz"))
+    sd2, td2, _ = _pair(mesh, v0, reorder=True, taps=False)
+    t = sd2.load_checkpoint(str(tmp_path / "ck.npz"))
+    assert abs(t - 15 * 2e-3) < 1e-15
+    Solvers.run(td2, "ssprk2", 25, dt=2e-3)
+    np.testing.assert_array_equal(sd2.GetVolField(), straight)
