@@ -155,3 +155,74 @@ def test_checkpoint_restart_is_exact(cases, tmp_path):
     assert abs(t - 15 * 2e-3) < 1e-15
     Solvers.run(td2, "ssprk2", 25, dt=2e-3)
     np.testing.assert_array_equal(sd2.GetVolField(), straight)
+
+
+@pytest.mark.parametrize("ni,nj", [(1, 1), (2, 1), (3, 3)])
+def test_tiny_meshes_all_boundary(ni, nj):
+    """Edge cases: meshes where every (or almost every) triangle touches the wall, random wet / dry /
+    nearly dry states, with Coriolis: GPU == oracle."""
+    from swe_fvm_b200 import StructTriangMesh
+    from swe_fvm_b200.solver import Solvers
+    mesh = StructTriangMesh(ni, nj, 0.7)
+    rng = np.random.default_rng(ni * 10 + nj)
+    mesh.geometry[:, 2] = rng.uniform(-1.0, 0.2, mesh.nn)
+    cb = mesh.centroids()[:, 2]
+    v0 = np.zeros((mesh.nt, 3))
+    depth = rng.choice([0.0, 1e-13, 5e-4, 0.05, 0.6], mesh.nt)
+    v0[:, 0] = cb + depth
+    v0[:, 1:] = rng.uniform(-0.3, 0.3, (mesh.nt, 2)) * (depth[:, None] > 1e-12)
+    sd, td, ref = _pair(mesh, v0, cor=0.5)
+    for _ in range(25):
+        Solvers.SSPRK3(td, 5e-3)
+        ref.step(2, 1, 2, 5e-3)
+    np.testing.assert_array_equal(sd.GetVolField(), ref.get_state())
+    assert np.isfinite(sd.GetVolField()).all()
+
+
+def test_all_dry_and_zero_steps(cases):
+    from swe_fvm_b200.solver import Solvers
+    mesh, case, v0 = cases["thacker64"]
+    dry = v0.copy()
+    dry[:, 0] = mesh.centroids()[:, 2]
+    dry[:, 1:] = 0.0
+    sd, td, ref = _pair(mesh, dry, taps=False)
+    Solvers.run(td, "ssprk2", 0, dt=1e-3)       # zero steps: nothing happens
+    np.testing.assert_array_equal(sd.GetVolField(), dry)
+    Solvers.run(td, "ssprk2", 3, dt=1e-3)
+    ref.run(1, 1, 2, 3, 1e-3)
+    np.testing.assert_array_equal(sd.GetVolField(), ref.get_state())
+    np.testing.assert_array_equal(sd.GetVolField(), dry)  # a dry basin stays dry
+    assert td.CFLdt() == 0.15  # no wet edge: min_len keeps its reset value 1.0
+
+
+def test_non_finite_state_is_reported(cases):
+    """The device raises a flag when an update produces a non-finite state; swe_synchronize turns
+    it into SWE_ERR_NUMERIC (SolverError in the C++ shim) instead of silently continuing."""
+    from swe_fvm_b200 import SweError
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    mesh, case, v0 = cases["wet48"]
+    bad = v0.copy()
+    bad[mesh.nt // 2, 1] = np.nan
+    sd = SpaceDisc("hllc", "einfeldt", mesh, bad)
+    Solvers.SSPRK2(TimeDisc(sd), 1e-3)
+    with pytest.raises(SweError) as ei:
+        sd.synchronize()
+    assert ei.value.status == -4
+
+
+def test_argument_errors(cases):
+    from swe_fvm_b200 import SweError
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    mesh, case, v0 = cases["wet48"]
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0)
+    td = TimeDisc(sd)
+    with pytest.raises(SweError):
+        Solvers.SSPRK2(td, -1.0)
+    with pytest.raises(SweError):
+        sd._call("swe_step", 7, 1, 2, 1e-3)
+    with pytest.raises(SweError):
+        sd._call("swe_compute_fluxes", 5, 2)
+    with pytest.raises(SweError):
+        sd.GetEdgField()  # taps were not enabled
+    with pytest.raises(ValueError):
+        sd.SetVolField(v0[:-1])
