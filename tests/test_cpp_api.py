@@ -56,3 +56,17 @@ def test_cpp_driver_reproduces_reference_dumps(tmp_path):
     assert float(lake.split("max|u|,|v| = ")[1].split(",")[0]) < 1e-14
     th = [l for l in lines if l.startswith("TestThacker")][0]
     assert float(th.split("L2 error of h = ")[1].split(",")[0]) < 2e-2
+
+
+def test_cpp_host_api_without_gpu(tmp_path):
+    """Host-only parts of the C++ mirror: mesh classes, Domain geometry, the reference's proxy
+    assigners, Gmsh reader, analytic cases, flux tags (tests/cpp/host_api_test.cpp)."""
+    exe = str(tmp_path / "host_api_test")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp"), "-L" + os.path.join(ROOT, "swe_fvm_b200"), "-lswe_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "swe_fvm_b200"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, os.path.join(GOLDEN, "bowl.msh")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
