@@ -247,23 +247,30 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     if (3 * nt >= (int64_t)2147483647 || 2 * ne >= (int64_t)2147483647)
         return fail(SWE_ERR_INVALID, "swe_create: mesh too large for int32 device ids");
     // validate ids and boundary tags (only SOLID_WALL is implemented upstream, src/SpaceDisc.cpp:66-72)
-    for (int64_t e = 0; e < ne; ++e) {
-        const int64_t a = mesh->edge_elements[2 * e], b = mesh->edge_elements[2 * e + 1];
-        if (a < 0 || a >= nt || b >= nt) return fail(SWE_ERR_INVALID, "swe_create: edge_elements id out of range");
-        if (b < 0 && b != SWE_SOLID_WALL)
-            return fail(SWE_ERR_INVALID, "swe_create: only SOLID_WALL (-1) boundaries are supported");
-        if (mesh->edge_nodes[2 * e] < 0 || mesh->edge_nodes[2 * e] >= nn || mesh->edge_nodes[2 * e + 1] < 0 ||
-            mesh->edge_nodes[2 * e + 1] >= nn)
-            return fail(SWE_ERR_INVALID, "swe_create: edge_nodes id out of range");
-    }
-    for (int64_t k = 0; k < 3 * nt; ++k) {
-        if (mesh->element_nodes[k] < 0 || mesh->element_nodes[k] >= nn)
-            return fail(SWE_ERR_INVALID, "swe_create: element_nodes id out of range");
-        if (mesh->element_edges[k] < 0 || mesh->element_edges[k] >= ne)
-            return fail(SWE_ERR_INVALID, "swe_create: element_edges id out of range");
-        const int64_t nb = mesh->element_neighbours[k];
-        if (nb >= nt || (nb < 0 && nb != SWE_SOLID_WALL))
-            return fail(SWE_ERR_INVALID, "swe_create: element_neighbours id out of range / unsupported boundary");
+    {
+        int bad = 0;  // 1 edge_elements, 2 boundary tag, 3 edge_nodes, 4 element_nodes, 5 element_edges, 6 neighbours
+#pragma omp parallel for schedule(static) reduction(max : bad)
+        for (int64_t e = 0; e < ne; ++e) {
+            const int64_t a = mesh->edge_elements[2 * e], b = mesh->edge_elements[2 * e + 1];
+            if (a < 0 || a >= nt || b >= nt) bad = std::max(bad, 1);
+            else if (b < 0 && b != SWE_SOLID_WALL) bad = std::max(bad, 2);
+            if (mesh->edge_nodes[2 * e] < 0 || mesh->edge_nodes[2 * e] >= nn || mesh->edge_nodes[2 * e + 1] < 0 ||
+                mesh->edge_nodes[2 * e + 1] >= nn)
+                bad = std::max(bad, 3);
+        }
+        if (bad == 1) return fail(SWE_ERR_INVALID, "swe_create: edge_elements id out of range");
+        if (bad == 2) return fail(SWE_ERR_INVALID, "swe_create: only SOLID_WALL (-1) boundaries are supported");
+        if (bad == 3) return fail(SWE_ERR_INVALID, "swe_create: edge_nodes id out of range");
+#pragma omp parallel for schedule(static) reduction(max : bad)
+        for (int64_t k = 0; k < 3 * nt; ++k) {
+            if (mesh->element_nodes[k] < 0 || mesh->element_nodes[k] >= nn) bad = std::max(bad, 4);
+            if (mesh->element_edges[k] < 0 || mesh->element_edges[k] >= ne) bad = std::max(bad, 5);
+            const int64_t nb = mesh->element_neighbours[k];
+            if (nb >= nt || (nb < 0 && nb != SWE_SOLID_WALL)) bad = std::max(bad, 6);
+        }
+        if (bad == 4) return fail(SWE_ERR_INVALID, "swe_create: element_nodes id out of range");
+        if (bad == 5) return fail(SWE_ERR_INVALID, "swe_create: element_edges id out of range");
+        if (bad == 6) return fail(SWE_ERR_INVALID, "swe_create: element_neighbours id out of range / unsupported boundary");
     }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -345,6 +352,8 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     // ---- host-side conversion to int32 SoA in device numbering ----
     {
         std::vector<int> h_tp((size_t)3 * nt), h_tt((size_t)3 * nt), h_te((size_t)3 * nt);
+        int inconsistent = 0;
+#pragma omp parallel for schedule(static) reduction(max : inconsistent)
         for (int64_t t = 0; t < nt; ++t) {
             const int d = cell_new[t];
             for (int k = 0; k < 3; ++k) {
@@ -353,12 +362,13 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
                 h_tt[(size_t)k * nt + d] = nb >= 0 ? cell_new[nb] : (int)nb;
                 const int64_t e = mesh->element_edges[3 * t + k];
                 const bool first = mesh->edge_elements[2 * e] == t;
-                if (!first && mesh->edge_elements[2 * e + 1] != t) {
-                    destroy_ctx(c);
-                    return fail(SWE_ERR_INVALID, "swe_create: element_edges / edge_elements are inconsistent");
-                }
+                if (!first && mesh->edge_elements[2 * e + 1] != t) inconsistent = 1;
                 h_te[(size_t)k * nt + d] = first ? edge_new[e] : ~edge_new[e];
             }
+        }
+        if (inconsistent) {
+            destroy_ctx(c);
+            return fail(SWE_ERR_INVALID, "swe_create: element_edges / edge_elements are inconsistent");
         }
         CREATE_TRY(dalloc(&c->tp, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->tt, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->te, (size_t)3 * nt));
         CREATE_TRY(cudaMemcpy(c->tp, h_tp.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
@@ -379,6 +389,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     {
         std::vector<int> h((size_t)4 * ne);
         int *ep0 = h.data(), *ep1 = ep0 + ne, *et0 = ep1 + ne, *et1 = et0 + ne;
+#pragma omp parallel for schedule(static)
         for (int64_t e = 0; e < ne; ++e) {
             const int d = edge_new[e];
             ep0[d] = node_new[mesh->edge_nodes[2 * e]]; ep1[d] = node_new[mesh->edge_nodes[2 * e + 1]];
@@ -392,6 +403,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     }
     {
         std::vector<double> h((size_t)4 * nn);
+#pragma omp parallel for schedule(static)
         for (int64_t p = 0; p < nn; ++p) {
             double *q = &h[(size_t)4 * node_new[p]];
             q[0] = mesh->geometry[3 * p]; q[1] = mesh->geometry[3 * p + 1]; q[2] = mesh->geometry[3 * p + 2]; q[3] = 0.;
