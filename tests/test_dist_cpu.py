@@ -79,3 +79,34 @@ def test_strip_decomposition_lists_are_consistent():
     et = d.mesh.edge_elements
     touch = d.owned[et[:, 0]] | np.where(et[:, 1] >= 0, d.owned[np.maximum(et[:, 1], 0)], False)
     np.testing.assert_array_equal(mask, touch)
+
+
+def test_cell_classes_mark_halo_dependent_stencils():
+    """Class 1 = the cell or one of its three edge neighbours is a halo (received) cell; class 0
+    cells can therefore be reconstructed before the halo of the previous stage has arrived."""
+    from swe_fvm_b200 import TriangMesh
+    from swe_fvm_b200 import dist as swd
+    n, world = 12, 3
+    for r in range(world):
+        d = swd.decompose_strips(n, n, 4.0 / n, r, world)
+        cls = d.cell_classes()
+        halo = np.zeros(d.mesh.nt, bool)
+        halo[d.recv_list()] = True
+        tt = d.mesh.element_neighbours
+        for i in range(d.mesh.nt):
+            dep = halo[i] or any(j >= 0 and halo[j] for j in tt[i])
+            assert cls[i] == int(dep)
+        assert (~d.owned == halo).all()  # every non-owned cell is received from some peer
+        assert cls[d.owned].sum() > 0 and (cls == 0).sum() > 0
+    bowl = TriangMesh.from_gmsh(os.path.join(GOLDEN, "bowl.msh"))
+    part = bowl.partition_rcb(2)
+    wants = []
+    for r in range(2):
+        sub = bowl.extract(part, r, swd.HALO_LAYERS)
+        gc, owner = np.array(sub.global_cells), np.array(sub.cell_owner)
+        wants.append({int(q): gc[owner == q] for q in np.unique(owner) if q != r})
+    for r in range(2):
+        d = swd.decompose_general(bowl, part, r, 2, all_gather_object=lambda w: wants)
+        cls = d.cell_classes()
+        assert set(np.nonzero(~d.owned)[0]) <= set(np.nonzero(cls == 1)[0])
+        assert 0 < cls.sum() < 0.2 * d.mesh.nt
