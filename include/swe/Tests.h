@@ -4,12 +4,19 @@
 // plain constructor arguments with the defaults suggested in SURVEY.md App. C.
 #pragma once
 #include "Bathymetry.h"
+#include "DimensionManager.h"
 #include "ValueField.h"
 
 class Test {
  protected:
     swe_case m_c{};
     Test(int kind, double mid_x, double mid_y, double length) { swe_case_defaults(&m_c, kind, mid_x, mid_y, length); }
+    // the reference's constructor (examples/Tests.h:13-17): cor, tau from [Common], unscaled as sources
+    Test(int kind, const Parser &par, const DimensionManager &dim, double mid_x, double mid_y)
+        : Test(kind, mid_x, mid_y, 2 * mid_x) {
+        m_c.cor = dim.Unscale<Scales::source>(par.Get("Common", "cor"));
+        m_c.tau = dim.Unscale<Scales::source>(par.Get("Common", "tau"));
+    }
 
  public:
     virtual ~Test() = default;
@@ -42,6 +49,8 @@ class Test {
 class LakeAtRestTest : public Test {
  public:
     LakeAtRestTest(double mid_x, double mid_y) : Test(SWE_CASE_LAKE_AT_REST, mid_x, mid_y, 2 * mid_x) {}
+    LakeAtRestTest(const Parser &par, const DimensionManager &dim, double mid_x, double mid_y)  // examples/Tests.h:34
+        : Test(SWE_CASE_LAKE_AT_REST, par, dim, mid_x, mid_y) {}
 };
 
 class ClassicThackerTest : public Test {
@@ -50,6 +59,14 @@ class ClassicThackerTest : public Test {
                        double p0 = 0., double q0 = 0.)
         : Test(SWE_CASE_CLASSIC_THACKER, mid_x, mid_y, 2 * mid_x) {
         m_c.cor = cor; m_c.tau = tau; m_c.delta = delta; m_c.H0 = H0; m_c.p0 = p0; m_c.q0 = q0;
+    }
+    // examples/Tests.h:242 with BowlTest (:49-51, [Common] delta) and ThackerTest (:138-142, [Thacker] H0 p0 q0)
+    ClassicThackerTest(const Parser &par, const DimensionManager &dim, double mid_x, double mid_y)
+        : Test(SWE_CASE_CLASSIC_THACKER, par, dim, mid_x, mid_y) {
+        m_c.delta = par.Get("Common", "delta");
+        m_c.H0 = dim.Unscale<Scales::height>(par.Get("Thacker", "H0"));
+        m_c.p0 = dim.Unscale<Scales::source>(par.Get("Thacker", "p0"));
+        m_c.q0 = dim.Unscale<Scales::source>(par.Get("Thacker", "q0"));
     }
 };
 

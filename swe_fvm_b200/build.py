@@ -52,6 +52,29 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def pybind_path() -> str:
+    import sysconfig
+    return os.path.join(os.path.dirname(_HERE), "pybind", "SWE_FVM" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind(force: bool = False) -> str:
+    """The pybind11 module SWE_FVM (pybind/swe_fvm_module.cpp) over the C++ host API; host-only C++."""
+    import sysconfig
+    import pybind11
+    root = os.path.dirname(_HERE)
+    src = os.path.join(root, "pybind", "swe_fvm_module.cpp")
+    out = pybind_path()
+    deps = [src, LIB] + [os.path.join(root, "include", "swe", f) for f in os.listdir(os.path.join(root, "include", "swe"))]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I" + pybind11.get_include(),
+           "-I" + sysconfig.get_paths()["include"], "-I" + os.path.join(root, "include"), src, "-L" + _HERE, "-lswe_b200",
+           "-Wl,-rpath," + _HERE, "-o", out]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     import sys
     build_lib(force=True, verbose="-v" in sys.argv)

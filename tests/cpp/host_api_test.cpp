@@ -87,6 +87,26 @@ int main(int argc, char **argv) {
     lake.SetBathymetry(ld);
     const VolumeField l0 = lake.InitialState(ld);
     for (Idx t = 0; t < ld.Mesh().NumTriangles(); ++t) CHECK(l0.w(t) == 0. && l0.u(t) == 0.);
+    // .ini Parser + DimensionManager + the reference's Test constructor signatures
+    {
+        const std::string ini = argc > 2 ? argv[2] : "examples/config.ini";
+        Parser parser(ini);
+        DimensionManager dimer(parser);
+        CHECK(parser.Get("Common", "delta") == 1.0 && parser.Get("Thacker", "H0") == 0.5);
+        bool perr = false;
+        try { parser.Get("Common", "nope"); } catch (const ParserError &) { perr = true; }
+        CHECK(perr);
+        perr = false;
+        try { Parser missing("/nonexistent.ini"); } catch (const ParserError &) { perr = true; }
+        CHECK(perr);
+        const DimensionManager d2(2.0, 10.0, 4.0);
+        CHECK(d2.Scale<Scales::height>(1.5) == 3.0 && d2.Unscale<Scales::length>(5.0) == 0.5);
+        CHECK(d2.Scale<Scales::source>(1.0) == 0.4 && d2.Unscale<Scales::time>(5.0) == 2.0);
+        ClassicThackerTest a(parser, dimer, 2., 2.), b(2., 2.);
+        for (double x : {1.7, 2.0, 2.2}) CHECK(a.h(x, 2.1, 0.3) == b.h(x, 2.1, 0.3) && a.u(x, 2.1, 0.3) == b.u(x, 2.1, 0.3));
+        LakeAtRestTest l2(parser, dimer, 2., 2.);
+        CHECK(l2.b(2., 2.) == -0.2);
+    }
     // flux tags keep the reference's spelling
     constexpr Fluxer f = Fluxes::HLLC<Wavespeeds::Einfeldt>;
     static_assert(f.flux == SWE_HLLC && f.wavespeed == SWE_EINFELDT, "tag mapping");

@@ -68,5 +68,6 @@ def test_cpp_host_api_without_gpu(tmp_path):
            "-Wl,-rpath," + os.path.join(ROOT, "swe_fvm_b200"), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([exe, os.path.join(GOLDEN, "bowl.msh")], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([exe, os.path.join(GOLDEN, "bowl.msh"), os.path.join(ROOT, "examples", "config.ini")],
+                       capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
