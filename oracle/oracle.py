@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         l.oracle_cfl_dt.argtypes = [C.c_void_p]
         for name in ("edge_states", "sources", "fluxes", "node_max_w", "draining_dt"):
             getattr(l, "oracle_get_" + name).argtypes = [C.c_void_p, _D]
+        l.oracle_get_branch_counts.argtypes = [C.c_void_p, _I64]
         l.oracle_get_cell_class.argtypes = [C.c_void_p, C.POINTER(C.c_int8)]
         l.oracle_get_geometry.argtypes = [C.c_void_p, _D, _D, _D, _D, _D, _D]
         l.oracle_diagnostics.argtypes = [C.c_void_p, _D]
@@ -57,6 +58,14 @@ def lib() -> C.CDLL:
         l.oracle_ilog2_trunc.argtypes = [C.c_double]
         l.oracle_bisection_cubic.restype = C.c_double
         l.oracle_bisection_cubic.argtypes = [C.c_double] * 5
+        l.oracle_bisection_cubic2.restype = C.c_double
+        l.oracle_bisection_cubic2.argtypes = [C.c_double] * 5 + [C.c_int]
+        l.oracle_rhs.argtypes = [C.c_void_p, C.c_int64, C.c_double, _D]
+        l.oracle_edge_flux.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, _D, _D]
+        l.oracle_wavespeeds.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _D]
+        l.oracle_get_draining_dt_live.argtypes = [C.c_void_p, _D]
+        l.oracle_assign_cons.argtypes = [C.c_void_p, C.c_int64, _D]
+        l.oracle_get_cons.argtypes = [C.c_void_p, C.c_int64, _D]
         l.oracle_gradient.argtypes = [_D, _D]
         l.oracle_elem_flux.argtypes = [_D, _D, _D]
         l.oracle_reconstruct.argtypes = [C.c_void_p, C.c_int, C.c_int64, _D, _D]
@@ -154,6 +163,43 @@ class Oracle:
 
     def draining_dt(self):
         return self._get("draining_dt", (self.nt,))
+
+    def draining_dt_live(self):
+        return self._get("draining_dt_live", (self.nt,))
+
+    def rhs(self, i, dt):
+        out = np.empty(3)
+        lib().oracle_rhs(self._h, i, dt, _d(out))
+        return out
+
+    def edge_flux(self, flux, ws, e, with_r=True):
+        F = np.empty(3)
+        r = C.c_double(1.0)
+        lib().oracle_edge_flux(self._h, flux, ws, e, _d(F), C.byref(r) if with_r else None)
+        return F, r.value
+
+    def wavespeeds(self, ws, ul, hl, ur, hr):
+        a = np.empty(2)
+        lib().oracle_wavespeeds(self._h, ws, ul, hl, ur, hr, _d(a))
+        return a
+
+    def assign_cons(self, i, cons3):
+        v = np.ascontiguousarray(cons3, dtype=np.float64)
+        lib().oracle_assign_cons(self._h, i, _d(v))
+
+    def get_cons(self, i):
+        out = np.empty(3)
+        lib().oracle_get_cons(self._h, i, _d(out))
+        return out
+
+    BRANCHES = ("pw1_submerged", "pw1_cbrt", "pw1_bisection", "fw_dry_neighbour", "fw_partwet_neighbour", "fw_vertex_zeroed",
+                "fw_tvd_off", "pw2_to_pw1", "pw2_one_wet", "pw2_three_wet", "pw2_two_wet", "pw2_two_wet_fallback")
+
+    def branch_counts(self):
+        """Branch-hit counters of the last compute_interface_values (see swe_oracle.cpp `branch`)."""
+        out = np.zeros(12, dtype=np.int64)
+        lib().oracle_get_branch_counts(self._h, _i(out))
+        return dict(zip(self.BRANCHES, out.tolist()))
 
     def cell_class(self):
         out = np.empty(self.nt, dtype=np.int8)

@@ -80,10 +80,10 @@ struct CubicPoly {
 
 // src/PointOperations.cpp:26-40
 template <class F>
-double Bisection(const F &f, double xmin = 0., double xmax = 1., const int accuracy = 50) {
+double Bisection(const F &f, double xmin = 0., double xmax = 1., const int accuracy = 50, bool libm = false) {
     if (std::signbit(f(xmin)) == std::signbit(f(xmax)))
         return (std::fabs(f(xmin)) < std::fabs(f(xmax))) ? xmin : xmax;
-    int n = accuracy + ilog2_trunc(xmax - xmin);
+    int n = accuracy + (libm ? static_cast<int>(std::log2(xmax - xmin)) : ilog2_trunc(xmax - xmin));
     double x = xmin;
     for (int i = 0; i <= n; i++) {
         x = 0.5 * (xmin + xmax);
@@ -110,6 +110,12 @@ inline void Gradient(const double P0[3], const double P1[3], const double P2[3],
 
 inline double Det(const double a[2], const double b[2]) { return a[0] * b[1] - b[0] * a[1]; }  // :8-10
 
+// which branch the last reconstruction call of this thread took (debug tap for the tests that
+// assert every branch of PartWet1 / PartWet2 / FullWet is exercised)
+struct Trace { int pw1 = -1, pw2 = -1, fw = 0; };
+thread_local Trace g_trace;
+enum { FW_DRY_NB = 1, FW_PW_NB = 2, FW_VERTEX_ZERO = 4, FW_TVD_OFF = 8 };
+
 struct MUSCL {  // include/MUSCLObject.h:15-55
     double o[3];
     double G[3][2];
@@ -126,6 +132,8 @@ struct Oracle {
     int recon = 0;       // S2: 0 = repaired (w,u,v plane gradients), 1 = as written, 2 = first order
     int roe_fix = 0;     // S5: 0 = cl*ur as written, 1 = cr*ur
     int cfl_abs = 0;     // S6: 0 = signed max as written, 1 = magnitudes
+    int pw2 = 0;         // S3: 0 = PartWet2 points(r,c) read as (point, coordinate), 1 = as written
+    int libm = 0;        // S9: 0 = det_cbrt / ilog2_trunc (shared with the device), 1 = libm cbrt, (int)log2
     int threads = 1;
     // geometry, computed once with the reference's formulas (the reference recomputes them on
     // every access: src/Bathymetry.cpp:20-31,69-90)
@@ -135,6 +143,24 @@ struct Oracle {
     std::vector<double> vol, edg, src, f, maxwp, volref;
     std::vector<uint8_t> cfl_mask;
     double min_len = 1.;
+    // branch-hit counters of the last ComputeInterfaceValues (see Trace): [0..2] pass-1 PartWet1 of a
+    // part-wet cell (submerged / cbrt / bisection), [3..6] full-wet cells (dry neighbour / part-wet
+    // neighbour / vertex check zeroed the gradient / TVD switched a component off), [7..11] pass-2
+    // PartWet2 (early PartWet1 / 1 wet / 3 wet / 2 wet / 2-wet fallback)
+    int64_t branch[12] = {0};
+    void count_pass1(int cls) {
+        int64_t add[12] = {0};
+        if (cls == 1) add[g_trace.pw1] = 1;
+        else if (cls == 2) for (int b = 0; b < 4; ++b) add[3 + b] = (g_trace.fw >> b) & 1;
+        for (int b = 0; b < 12; ++b) if (add[b]) {
+#pragma omp atomic
+            branch[b] += 1;
+        }
+    }
+    void count_pass2() {
+#pragma omp atomic
+        branch[7 + g_trace.pw2] += 1;
+    }
 
     // ---- Domain (src/Bathymetry.cpp) ----
     const double *P(Idx n) const { return &geom[3 * n]; }
@@ -173,10 +199,12 @@ struct Oracle {
         for (Idx e = 0; e < ne; ++e) {
             double tan[2];
             tang(e, et[2 * e], tan);
-            norm0[2 * e] = tan[1]; norm0[2 * e + 1] = -tan[0];  // src/Bathymetry.cpp:78-80
+            // src/Bathymetry.cpp:78-80: [[0, 1], [-1, 0]] * Tang, multiplied out literally so that
+            // even the signs of zero components are upstream's
+            norm0[2 * e] = 0. * tan[0] + 1. * tan[1]; norm0[2 * e + 1] = -1. * tan[0] + 0. * tan[1];
             if (et[2 * e + 1] >= 0) {
                 tang(e, et[2 * e + 1], tan);
-                norm1[2 * e] = tan[1]; norm1[2 * e + 1] = -tan[0];
+                norm1[2 * e] = 0. * tan[0] + 1. * tan[1]; norm1[2 * e + 1] = -1. * tan[0] + 0. * tan[1];
             }
         }
         for (Idx t = 0; t < nt; ++t)  // src/TriangMesh.cpp:18-23
@@ -233,14 +261,16 @@ struct Oracle {
         const double wi = vol[3 * i], hi = vol[3 * i] - vb(i);
         double w_rec;
         if (wi >= b13) {
-            w_rec = wi;
+            w_rec = wi; g_trace.pw1 = 0;
         } else if (wi <= b_delimiter) {
-            w_rec = b23 + det_cbrt(3. * hi * (b13 - b23) * (b12 - b23));
+            g_trace.pw1 = 1;
+            w_rec = b23 + (libm ? std::cbrt(3. * hi * (b13 - b23) * (b12 - b23)) : det_cbrt(3. * hi * (b13 - b23) * (b12 - b23)));
         } else {
             double a = -3. * b13;
             double b = 3. * (b12 * b13 + b13 * b23 - b12 * b23);
             double c = (b13 - b23) * (3. * hi * (b13 - b12) - b12 * (b12 + b23)) - b23 * b23 * b13;
-            w_rec = Bisection(CubicPoly(c, b, a), b12, b13);
+            g_trace.pw1 = 2;
+            w_rec = Bisection(CubicPoly(c, b, a), b12, b13, 50, libm != 0);
         }
         MUSCL m{};
         m.i = i;
@@ -254,14 +284,17 @@ struct Oracle {
         MUSCL m{};
         m.i = i;
         for (int c = 0; c < 3; ++c) m.o[c] = pi[c];
+        g_trace.fw = 0;
         double X[3][3];  // grad_points: (x, y, bed) per support point
         double V[3][3];  // grad_values per support point
         for (int k = 0; k < 3; ++k) {
             if (IsFullWetCell(it[k])) {
                 for (int c = 0; c < 3; ++c) { X[k][c] = T(it[k])[c]; V[k][c] = vol[3 * it[k] + c]; }
             } else if (IsDryCell(vol, it[k])) {
+                g_trace.fw |= FW_DRY_NB;
                 return m;  // zero gradient
             } else {
+                g_trace.fw |= FW_PW_NB;
                 MUSCL nb = ReconstructPartWetCell1(it[k]);
                 const double *pt = E(ie[k]);
                 double a[3];
@@ -294,7 +327,7 @@ struct Oracle {
             double hp = wp - P(ip[k])[2];
             if (!IsWet(hp)) all_wet = false;
         }
-        if (!all_wet) for (int c = 0; c < 3; ++c) df[c][0] = df[c][1] = 0.;
+        if (!all_wet) { g_trace.fw |= FW_VERTEX_ZERO; for (int c = 0; c < 3; ++c) df[c][0] = df[c][1] = 0.; }
         // on/off TVD limiter (:74-81)
         double TVD[3] = {1., 1., 1.};
         for (int k = 0; k < 3; ++k) {
@@ -304,7 +337,7 @@ struct Oracle {
                 double vtmin = std::min(pi[c], pn[c]);
                 double vtmax = std::max(pi[c], pn[c]);
                 double vek = pi[c] + (df[c][0] * dx + df[c][1] * dy);
-                if (!((vtmin <= vek) && (vek <= vtmax))) TVD[c] = 0.;
+                if (!((vtmin <= vek) && (vek <= vtmax))) { TVD[c] = 0.; g_trace.fw |= FW_TVD_OFF; }
             }
         }
         for (int c = 0; c < 3; ++c) { m.G[c][0] = TVD[c] * df[c][0]; m.G[c][1] = TVD[c] * df[c][1]; }
@@ -318,7 +351,7 @@ struct Oracle {
         if (P(ip[0])[2] > P(ip[1])[2]) std::swap(ip[0], ip[1]);
         const double *Q0 = P(ip[0]), *Q1 = P(ip[1]), *Q2 = P(ip[2]);
         double b23 = Q0[2], b12 = Q1[2], b13 = Q2[2];
-        if ((vol[3 * i] > b13) || (b13 - b23 < tol)) return ReconstructPartWetCell1(i);
+        if ((vol[3 * i] > b13) || (b13 - b23 < tol)) { g_trace.pw2 = 0; return ReconstructPartWetCell1(i); }
 
         double w23 = maxwp[ip[0]];
         double h23 = w23 - b23;
@@ -328,28 +361,35 @@ struct Oracle {
         double hi = vol[3 * i] - vb(i);
         double ratio_h = hi / h23;
 
-        double S0[3] = {Q0[0], Q0[1], w23}, S1[3], S2[3];
+        // as written (pw2 == 1) the scalar accesses points(0,2), points(1,2) hit x/y entries of the
+        // third point that the following points.col(2) = ... overwrites: S0.z stays b23, S1.z stays b12
+        double S0[3] = {Q0[0], Q0[1], pw2 ? Q0[2] : w23}, S1[3], S2[3];
         if (hi <= h_delimiter1) {  // 1 point wet, 2 dry
+            g_trace.pw2 = 1;
             double k2 = std::sqrt(3. * ratio_h / ratio_b);
             for (int c = 0; c < 3; ++c) S1[c] = k2 * Q1[c] + (1. - k2) * Q0[c];
             double k3 = std::sqrt(3. * ratio_h * ratio_b);
             for (int c = 0; c < 3; ++c) S2[c] = k3 * Q2[c] + (1. - k3) * Q0[c];
         } else if (hi >= h_delimiter2) {  // 3 points wet
+            g_trace.pw2 = 2;
             double delta_w = 1.5 * (hi - h_delimiter2);
             S1[0] = Q1[0]; S1[1] = Q1[1]; S1[2] = Q1[2];
-            S1[2] += delta_w;
-            S1[2] += (1. - ratio_b) * h23;
+            if (!pw2) {
+                S1[2] += delta_w;
+                S1[2] += (1. - ratio_b) * h23;
+            }
             S2[0] = Q2[0]; S2[1] = Q2[1]; S2[2] = Q2[2];
             S2[2] += delta_w;
         } else {  // 2 points wet, 1 dry
+            g_trace.pw2 = 3;
             double alpha = 3. * ratio_h;
             double beta = (b13 - b12) / (b13 - b23);
-            double k1 = 1. - Bisection(CubicPoly{(1. + beta - alpha) / (beta * beta), (alpha - 3.) / beta});
-            if (k1 < tol) return ReconstructPartWetCell1(i);
+            double k1 = 1. - Bisection(CubicPoly{(1. + beta - alpha) / (beta * beta), (alpha - 3.) / beta}, 0., 1., 50, libm != 0);
+            if (k1 < tol) { g_trace.pw2 = 4; return ReconstructPartWetCell1(i); }
             double k3 = 1. - beta * (1. - k1);
             double bp1 = k1 * b13 + (1. - k1) * b12;
             S1[0] = Q1[0]; S1[1] = Q1[1];
-            S1[2] = b12 + (k1 / k3) * beta * h23;
+            S1[2] = pw2 ? Q1[2] : b12 + (k1 / k3) * beta * h23;
             S2[0] = k1 * Q2[0] + (1. - k1) * Q1[0];
             S2[1] = k1 * Q2[1] + (1. - k1) * Q1[1];
             S2[2] = bp1;
@@ -405,26 +445,24 @@ struct Oracle {
 
     void ComputeInterfaceValues() {  // src/SpaceDisc.cpp:33-52
         for (Idx n = 0; n < nn; ++n) maxwp[n] = geom[3 * n + 2];
+        for (int b = 0; b < 12; ++b) branch[b] = 0;
+        auto pass1 = [this](Idx i) {
+            if (IsDryCell(vol, i)) { UpdateInterfaceValues(ReconstructDryCell(i), true); }
+            else if (!IsFullWetCell(i)) { MUSCL m = ReconstructPartWetCell1(i); count_pass1(1); UpdateInterfaceValues(m, true); }
+            else { MUSCL m = ReconstructFullWetCell(i); count_pass1(2); UpdateInterfaceValues(m, true); }
+        };
         if (sequential) {
-            for (Idx i = 0; i < nt; ++i) {
-                if (IsDryCell(vol, i)) UpdateInterfaceValues(ReconstructDryCell(i), true);
-                else if (!IsFullWetCell(i)) UpdateInterfaceValues(ReconstructPartWetCell1(i), true);
-                else UpdateInterfaceValues(ReconstructFullWetCell(i), true);
-            }
+            for (Idx i = 0; i < nt; ++i) pass1(i);
             for (Idx i = 0; i < nt; ++i)
-                if (IsPartWetCell(i)) UpdateInterfaceValues(ReconstructPartWetCell2(i), true);
+                if (IsPartWetCell(i)) { MUSCL m = ReconstructPartWetCell2(i); count_pass2(); UpdateInterfaceValues(m, true); }
             return;
         }
         // S8 (Jacobi): pass 2 reads the node maxima of pass 1 only and does not update them.
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
-        for (Idx i = 0; i < nt; ++i) {
-            if (IsDryCell(vol, i)) UpdateInterfaceValues(ReconstructDryCell(i), true);
-            else if (!IsFullWetCell(i)) UpdateInterfaceValues(ReconstructPartWetCell1(i), true);
-            else UpdateInterfaceValues(ReconstructFullWetCell(i), true);
-        }
+        for (Idx i = 0; i < nt; ++i) pass1(i);
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
         for (Idx i = 0; i < nt; ++i)
-            if (IsPartWetCell(i)) UpdateInterfaceValues(ReconstructPartWetCell2(i), false);
+            if (IsPartWetCell(i)) { MUSCL m = ReconstructPartWetCell2(i); count_pass2(); UpdateInterfaceValues(m, false); }
     }
 
     // ---- include/SpaceDisc.h:4-18 ----
@@ -665,6 +703,8 @@ int oracle_set_option(void *p, const char *key, int value) {
     else if (!std::strcmp(key, "recon")) o->recon = value;
     else if (!std::strcmp(key, "roe_fix")) o->roe_fix = value;
     else if (!std::strcmp(key, "cfl_abs")) o->cfl_abs = value;
+    else if (!std::strcmp(key, "pw2")) o->pw2 = value;
+    else if (!std::strcmp(key, "libm")) o->libm = value;
     else if (!std::strcmp(key, "threads")) {
 #ifdef _OPENMP
         o->threads = value > 0 ? value : omp_get_max_threads();
@@ -721,6 +761,10 @@ void oracle_get_draining_dt(void *p, double *out) {
     const std::vector<double> &ref = o->sequential ? o->vol : o->volref;
     for (Idx i = 0; i < o->nt; ++i) out[i] = o->ComputeDrainingDt(ref, i);
 }
+void oracle_get_branch_counts(void *p, int64_t *out12) {
+    Oracle *o = static_cast<Oracle *>(p);
+    for (int b = 0; b < 12; ++b) out12[b] = o->branch[b];
+}
 void oracle_get_cell_class(void *p, int8_t *out) {
     Oracle *o = static_cast<Oracle *>(p);
     for (Idx i = 0; i < o->nt; ++i) out[i] = o->IsDryCell(o->vol, i) ? 0 : (o->IsFullWetCell(i) ? 2 : 1);
@@ -755,6 +799,28 @@ void oracle_diagnostics(void *p, double out[6]) {
 double oracle_cbrt(double x) { return det_cbrt(x); }
 int oracle_ilog2_trunc(double x) { return ilog2_trunc(x); }
 double oracle_bisection_cubic(double d, double c, double b, double lo, double hi) { return Bisection(CubicPoly(d, c, b), lo, hi); }
+double oracle_bisection_cubic2(double d, double c, double b, double lo, double hi, int libm) {
+    return Bisection(CubicPoly(d, c, b), lo, hi, 50, libm != 0);
+}
+// TimeDisc::RHS(i, dt) / one edge flux / wavespeeds on the current fields (live state)
+void oracle_rhs(void *p, int64_t i, double dt, double *out3) {
+    Oracle *o = static_cast<Oracle *>(p);
+    o->RHS(o->vol, i, dt, out3);
+}
+void oracle_edge_flux(void *p, int flux, int ws, int64_t e, double *F3, double *r) {
+    Oracle *o = static_cast<Oracle *>(p);
+    o->Flux(flux, ws, e, o->et[2 * e], o->et[2 * e + 1], r, F3);
+}
+void oracle_wavespeeds(void *p, int ws, double ul, double hl, double ur, double hr, double *a2) {
+    static_cast<Oracle *>(p)->Wavespeeds(ws, ul, hl, ur, hr, a2);
+}
+void oracle_get_draining_dt_live(void *p, double *out) {
+    Oracle *o = static_cast<Oracle *>(p);
+    for (Idx i = 0; i < o->nt; ++i) out[i] = o->ComputeDrainingDt(o->vol, i);
+}
+// ConsAssigner::operator= / Get and PrimAssigner on cell i
+void oracle_assign_cons(void *p, int64_t i, const double *U3) { static_cast<Oracle *>(p)->cons_set(i, U3); }
+void oracle_get_cons(void *p, int64_t i, double *U3) { Oracle *o = static_cast<Oracle *>(p); o->cons_get(o->vol, i, U3); }
 void oracle_gradient(const double *P9, double *g2) { Gradient(P9, P9 + 3, P9 + 6, g2); }
 void oracle_elem_flux(const double *n2, const double *U3, double *F3) { Oracle::ElemFlux(n2, U3, F3); }
 // reconstruction of one cell: kind 0 dry, 1 partwet1, 2 fullwet, 3 partwet2 -> origin(3), G(6)

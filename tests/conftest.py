@@ -50,3 +50,53 @@ def rel_l2(a, b):
     d = np.linalg.norm(np.asarray(a) - np.asarray(b))
     n = np.linalg.norm(np.asarray(b))
     return d / n if n > 0 else d
+
+
+def random_front_state(mesh, T, seed, level=0.0, amp=0.3):
+    """A rough free surface cutting the bed: wet, dry and part-wet cells with non-zero velocities."""
+    rng = np.random.default_rng(seed)
+    w = level + amp * np.sin(1.3 * T[:, 0] + seed) * np.cos(0.9 * T[:, 1]) + 0.02 * rng.standard_normal(mesh.nt)
+    h = np.maximum(w - T[:, 2], 0.0)
+    u, v = 0.3 * rng.standard_normal(mesh.nt), 0.3 * rng.standard_normal(mesh.nt)
+    u[h <= 0], v[h <= 0] = 0.0, 0.0
+    return np.stack([h + T[:, 2], u, v], 1)
+
+
+def crafted_branch_state(mesh, T):
+    """Isolated wet cells on a dry sloping bed whose levels sit exactly on (or a few ulps from) the
+    switching points of ReconstructPartWetCell1/2 (src/MUSCLObject.cpp:100-108,127,145-171): w = b13
+    (highest vertex, -> pass-2 'three wet' branch) and w = b_delimiter +- k ulp (-> the k1 < tol
+    fall-back of the 'two wet' branch). Those branches are practically unreachable otherwise."""
+    bn = np.asarray(mesh.geometry)[:, 2][np.asarray(mesh.element_nodes)]
+    b13, b23 = bn.max(1), bn.min(1)
+    b12 = 3 * T[:, 2] - b23 - b13
+    bdel = b12 + (1. / 3.) * (b13 - b12) * (b13 - b12) / (b13 - b23)
+    w = T[:, 2].copy()
+    tt, tp = np.asarray(mesh.element_neighbours), np.asarray(mesh.element_nodes)
+    interior = (tt >= 0).all(1) & (b13 - b23 > 1e-6)
+    n2c = {}
+    for i in range(mesh.nt):
+        for p in tp[i]:
+            n2c.setdefault(int(p), []).append(i)
+    blocked = np.zeros(mesh.nt, bool)
+    picked = []
+    for i in np.where(interior)[0]:
+        if blocked[i]:
+            continue
+        picked.append(i)
+        for p in tp[i]:
+            blocked[n2c[int(p)]] = True
+    for idx, i in enumerate(picked):
+        m = idx % 12
+        if m < 3:
+            w[i] = b13[i]
+        elif m < 10:
+            w[i] = bdel[i]
+            for _ in range(abs(m - 6)):
+                w[i] = np.nextafter(w[i], np.inf if m > 6 else -np.inf)
+        else:
+            w[i] = bdel[i] * (1 + 1e-12 * (m - 10.5))
+    st = np.stack([w, np.zeros(mesh.nt), np.zeros(mesh.nt)], 1)
+    st[picked, 1] = 0.1
+    st[picked, 2] = -0.05
+    return st
