@@ -231,6 +231,9 @@ def run_gpu(args):
     sd = SpaceDisc("hllc", "einfeldt", mesh, None, device=local_rank, reorder=args.reorder,
                    cell_class=(dec.cell_classes() if dec is not None else None))
     sd.set_stream(torch.cuda.current_stream().cuda_stream)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        sd.set_option(k, int(v))
     td = TimeDisc(sd)
     pin_in = torch.from_numpy(v0).pin_memory()
     pin_out = torch.empty_like(pin_in).pin_memory()
@@ -396,6 +399,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="swe_set_option key=value (A/B runs), repeatable")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange with interior work")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 halo transport: p2p = pack kernel stores into the peer GPU's buffer over NVLink "

@@ -69,7 +69,12 @@ typedef enum swe_wavespeed { SWE_RUSANOV = 0, SWE_DAVIS = 1, SWE_EINFELDT = 2 } 
 enum { SWE_SOLID_WALL = -1, SWE_FREE_FLOW = -2, SWE_PERIODIC = -3, SWE_CUSTOM = -4 };
 
 /* Mesh + bathymetry exactly as the reference's Topology/Domain take them. All arrays are
- * HOST pointers, copied during swe_create (the caller may free them right after). */
+ * HOST pointers, copied during swe_create (the caller may free them right after).
+ * Local ordering (the convention of upstream's mesh builders, notebooks/topology.dat): for every cell t and
+ * k = 0,1,2, element_edges[t][k] joins element_nodes[t][k] and element_nodes[t][(k+1)%3], and
+ * element_neighbours[t][k] is the cell across that edge (or a negative boundary tag). swe_create checks this
+ * and returns SWE_ERR_INVALID otherwise (upstream itself would accept any local order because it looks the
+ * edge points up per edge; the kernels here take the edge midpoints from the cell's own nodes). */
 typedef struct swe_mesh {
     int64_t nn, ne, nt;
     const double *geometry;             /* 3 x nn column-major: (x, y, b) per node        */
@@ -159,8 +164,27 @@ SWE_API int swe_stage_update(swe_ctx *ctx, double a0, double a1, double dt_stage
 SWE_API int swe_stage_update_dev(swe_ctx *ctx, double a0, double a1, double coef);
 SWE_API int swe_set_dt(swe_ctx *ctx, double dt);
 SWE_API int swe_advance_dt(swe_ctx *ctx, int adaptive, double dt_fixed);
-/* keep the reconstructed edge-side w as well (needed only by swe_get_edge_states). */
+/* keep the reconstructed edge-side w as well (needed only by swe_get_edge_states) and count branch hits. */
 SWE_API int swe_enable_taps(swe_ctx *ctx, int on);
+
+/* Switches for the places where upstream HEAD is unfinished. Defaults = the
+ * repaired scheme; the alternatives reproduce upstream exactly as written and are bit-checked against
+ * upstream's own sources compiled in oracle/_ref (tests/test_ref_anchor.py, tests/test_gpu_parity.py):
+ *   "recon"   0 plane gradients of w,u,v from grad_values (S2, default) | 1 as written:
+ *             src/MUSCLObject.cpp:63-64 df.row(0) = Gradient(grad_points), u/v first order | 2 first order
+ *   "pw2"     0 ReconstructPartWetCell2 reads points(r,c) as (point, coordinate) (S3, default) |
+ *             1 as written (src/MUSCLObject.cpp:141-183)
+ *   "roe_fix" 0 Einfeldt Roe velocity cl*ur as written (src/Fluxes.cpp:22, default) | 1 cr*ur
+ *   "cfl_abs" 0 HLLC CFL candidate max(tol, max(al, ar)) as written (include/Fluxes.h:89, default) | 1 magnitudes */
+SWE_API int swe_set_option(swe_ctx *ctx, const char *key, int32_t value);
+SWE_API int swe_get_option(swe_ctx *ctx, const char *key, int32_t *value);
+/* Debug tap (taps enabled): how many cells took each branch in the last swe_compute_interface_values.
+ * [0..2] pass-1 ReconstructPartWetCell1 of a part-wet cell: submerged / closed form (cbrt) / bisection
+ * (src/MUSCLObject.cpp:100-108); [3..6] full-wet cells: dry neighbour (:52-53) / part-wet neighbour
+ * (:54-59) / gradient zeroed by the vertex check (:70-72) / a TVD component switched off (:80);
+ * [7..11] pass-2 ReconstructPartWetCell2: early PartWet1 (:127) / 1 vertex wet (:145) / 3 wet (:153) /
+ * 2 wet (:164) / 2-wet fall-back k1 < tol (:170). */
+SWE_API int swe_get_branch_counts(swe_ctx *ctx, int64_t out12[12]);
 
 /* Parity taps. HOST output buffers, caller numbering, reference layouts. */
 SWE_API int swe_get_edge_states(swe_ctx *ctx, double *edg_3x2ne); /* col = 2e + (from<to)  */

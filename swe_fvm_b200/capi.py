@@ -93,6 +93,9 @@ SYMBOLS = {
     "swe_set_dt": (C.c_int, [_P, C.c_double]),
     "swe_advance_dt": (C.c_int, [_P, C.c_int, C.c_double]),
     "swe_enable_taps": (C.c_int, [_P, C.c_int]),
+    "swe_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "swe_get_option": (C.c_int, [_P, C.c_char_p, _I32]),
+    "swe_get_branch_counts": (C.c_int, [_P, _I64]),
     "swe_get_edge_states": (C.c_int, [_P, _D]),
     "swe_get_sources": (C.c_int, [_P, _D]),
     "swe_get_fluxes": (C.c_int, [_P, _D]),

@@ -32,6 +32,9 @@ struct swe_ctx {
     double cor = 0, tau = 0;
     bool reordered = false;
     bool taps = false;
+    int opt_recon = 0, opt_pw2 = 0, opt_roe_fix = 0, opt_cfl_abs = 0;  // swe_set_option (semantic decisions S2/S3/S5/S6)
+    int opt_tiled = SWE_K1_TILED;                                      // K1 form: 1 = shared-memory staged tiles (TMA), 0 = gathers
+    unsigned long long *dbg = nullptr;                                 // branch-hit counters (taps)
     int class_first[6] = {0, 0, 0, 0, 0, 0};  // device cell range of every ordering class
     // device mesh
     int *tt = nullptr, *te = nullptr, *tp = nullptr, *slotL = nullptr, *slotR = nullptr;
@@ -119,6 +122,7 @@ static DevFields dev_fields(const swe_ctx *c) {
     s.ceh = c->ceh; s.ceu = c->ceu; s.cev = c->cev; s.cgx = c->cgx; s.cgy = c->cgy; s.cew = c->cew;
     s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.cls = c->cls; s.pw_list = c->pw_list; s.rs_list = c->rs_list;
     s.scal = c->scal; s.flags = c->flags;
+    s.dbg = c->dbg; s.recon = c->opt_recon; s.pw2 = c->opt_pw2;
     return s;
 }
 
@@ -194,7 +198,7 @@ static void destroy_ctx(swe_ctx *c) {
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
-                    c->send_cells, c->recv_cells};
+                    c->send_cells, c->recv_cells, c->dbg};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
@@ -214,14 +218,15 @@ static int ensure_stage(swe_ctx *c, size_t n_doubles) {
     return SWE_OK;
 }
 
-template <int FLUX>
+template <int FLUX, bool OPT>
 static void launch_flux_ws(swe_ctx *c, const DevMesh &m, const DevFields &s, int ws) {
     const int g = std::min(nblk(c->ne, kBlock), c->sms * SWE_K2_GRID_PER_SM);
     const double ac = std::fabs(c->cor);
+    const int rf = c->opt_roe_fix, ca = c->opt_cfl_abs;
     switch (ws) {
-        case SWE_RUSANOV: k_flux<FLUX, WS_RUSANOV><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
-        case SWE_DAVIS: k_flux<FLUX, WS_DAVIS><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
-        default: k_flux<FLUX, WS_EINFELDT><<<g, kBlock, 0, c->stream>>>(m, s, ac); break;
+        case SWE_RUSANOV: k_flux<FLUX, WS_RUSANOV, OPT><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca); break;
+        case SWE_DAVIS: k_flux<FLUX, WS_DAVIS, OPT><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca); break;
+        default: k_flux<FLUX, WS_EINFELDT, OPT><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca); break;
     }
 }
 
@@ -362,13 +367,23 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
                 h_tt[(size_t)k * nt + d] = nb >= 0 ? cell_new[nb] : (int)nb;
                 const int64_t e = mesh->element_edges[3 * t + k];
                 const bool first = mesh->edge_elements[2 * e] == t;
-                if (!first && mesh->edge_elements[2 * e + 1] != t) inconsistent = 1;
+                if (!first && mesh->edge_elements[2 * e + 1] != t) inconsistent = std::max(inconsistent, 1);
+                // local convention the kernels rely on (SURVEY App. B rules 3-4, notebooks/topology.dat):
+                // TriangEdges[k] joins TriangPoints[k] and TriangPoints[(k+1)%3], TriangTriangs[k] lies across it
+                const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
+                const int64_t p = mesh->element_nodes[3 * t + k], q = mesh->element_nodes[3 * t + (k + 1) % 3];
+                if (!((a == p && b == q) || (a == q && b == p))) inconsistent = std::max(inconsistent, 2);
+                const int64_t across = first ? mesh->edge_elements[2 * e + 1] : mesh->edge_elements[2 * e];
+                if (across != nb) inconsistent = std::max(inconsistent, 3);
                 h_te[(size_t)k * nt + d] = first ? edge_new[e] : ~edge_new[e];
             }
         }
         if (inconsistent) {
             destroy_ctx(c);
-            return fail(SWE_ERR_INVALID, "swe_create: element_edges / edge_elements are inconsistent");
+            return fail(SWE_ERR_INVALID,
+                        inconsistent == 1 ? "swe_create: element_edges / edge_elements are inconsistent"
+                        : inconsistent == 2 ? "swe_create: element_edges[k] must join element_nodes[k] and element_nodes[(k+1)%3]"
+                                            : "swe_create: element_neighbours[k] must be the cell across element_edges[k]");
         }
         CREATE_TRY(dalloc(&c->tp, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->tt, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->te, (size_t)3 * nt));
         CREATE_TRY(cudaMemcpy(c->tp, h_tp.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
@@ -530,7 +545,46 @@ SWE_API int swe_enable_taps(swe_ctx *c, int on) {
         CUDA_TRY(c, dalloc(&c->cew, (size_t)3 * c->nt));
         CUDA_TRY(c, cudaMemset(c->cew, 0, sizeof(double) * 3 * c->nt));
     }
+    if (on && !c->dbg) {
+        CUDA_TRY(c, dalloc(&c->dbg, (size_t)BR_COUNT));
+        CUDA_TRY(c, cudaMemset(c->dbg, 0, sizeof(unsigned long long) * BR_COUNT));
+    }
     c->taps = on != 0;
+    return SWE_OK;
+}
+
+// Semantic-decision switches; every value is bit-checked against the same oracle option.
+SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
+    if (!c || !key) return SWE_ERR_INVALID;
+    auto bad = [&](const char *why) { c->err = std::string("swe_set_option(") + key + "): " + why; return SWE_ERR_INVALID; };
+    if (!std::strcmp(key, "recon")) { if (value < 0 || value > 2) return bad("0 repaired, 1 as written, 2 first order"); c->opt_recon = value; }
+    else if (!std::strcmp(key, "pw2")) { if (value < 0 || value > 1) return bad("0 repaired, 1 as written"); c->opt_pw2 = value; }
+    else if (!std::strcmp(key, "roe_fix")) { if (value < 0 || value > 1) return bad("0 as written (cl*ur), 1 cr*ur"); c->opt_roe_fix = value; }
+    else if (!std::strcmp(key, "cfl_abs")) { if (value < 0 || value > 1) return bad("0 as written (signed max), 1 magnitudes"); c->opt_cfl_abs = value; }
+    else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > SWE_K1_TILED) return bad("0 gather kernel, 1 shared-memory staged tiles"); c->opt_tiled = value; }
+    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled)");
+    return SWE_OK;
+}
+SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
+    if (!c || !key || !value) return SWE_ERR_INVALID;
+    if (!std::strcmp(key, "recon")) *value = c->opt_recon;
+    else if (!std::strcmp(key, "pw2")) *value = c->opt_pw2;
+    else if (!std::strcmp(key, "roe_fix")) *value = c->opt_roe_fix;
+    else if (!std::strcmp(key, "cfl_abs")) *value = c->opt_cfl_abs;
+    else if (!std::strcmp(key, "k1_tiled")) *value = c->opt_tiled;
+    else { c->err = std::string("swe_get_option: unknown option ") + key; return SWE_ERR_INVALID; }
+    return SWE_OK;
+}
+// Branch-hit counters of the last swe_compute_interface_values (taps must be enabled): which branches of
+// ReconstructPartWetCell1/2 and ReconstructFullWetCell the cells took; slots as in swe_b200.h.
+SWE_API int swe_get_branch_counts(swe_ctx *c, int64_t out12[12]) {
+    if (!c || !out12) return SWE_ERR_INVALID;
+    if (!c->dbg || !c->taps) { c->err = "swe_get_branch_counts: call swe_enable_taps(ctx, 1) before computing"; return SWE_ERR_INVALID; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    unsigned long long h[BR_COUNT];
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->dbg, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < BR_COUNT; ++b) out12[b] = (int64_t)h[b];
     return SWE_OK;
 }
 
@@ -544,13 +598,35 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
     if (begin) {  // work-list counters: part-wet cells [1], generic-reconstruction cells [4]
         CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, sizeof(int), c->stream));
         CUDA_TRY(c, cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
+        if (c->taps) CUDA_TRY(c, cudaMemsetAsync(c->dbg, 0, sizeof(unsigned long long) * BR_COUNT, c->stream));
     }
     if (last > first) {
         int kt = kt_begin(c, KT_RECONSTRUCT);
         // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
         const int g1 = std::min(nblk(last - first, kK1Block), c->sms * SWE_K1_GRID_PER_SM);
-        if (c->taps) k_reconstruct<true><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last);
-        else k_reconstruct<false><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last);
+#if SWE_K1_TILED
+        const int ntiles = (last + kTile - 1) / kTile - first / kTile;
+        const int gt = std::min(ntiles, c->sms * SWE_K1_GRID_PER_SM);
+#define SWE_K1(TAPS) \
+        do { \
+            if (c->opt_tiled) { \
+                if (c->opt_recon == 0) k_reconstruct_tiled<TAPS, 0><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
+                else if (c->opt_recon == 1) k_reconstruct_tiled<TAPS, 1><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
+                else k_reconstruct_tiled<TAPS, 2><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
+            } else if (c->opt_recon == 0) k_reconstruct<TAPS, 0><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+            else if (c->opt_recon == 1) k_reconstruct<TAPS, 1><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+            else k_reconstruct<TAPS, 2><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+        } while (0)
+#else
+#define SWE_K1(TAPS) \
+        do { \
+            if (c->opt_recon == 0) k_reconstruct<TAPS, 0><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+            else if (c->opt_recon == 1) k_reconstruct<TAPS, 1><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+            else k_reconstruct<TAPS, 2><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+        } while (0)
+#endif
+        if (c->taps) SWE_K1(true); else SWE_K1(false);
+#undef SWE_K1
         kt_end(c, kt);
         if ((rc = launch_check(c, "k_reconstruct"))) return rc;
     }
@@ -598,7 +674,9 @@ SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     const int kt = kt_begin(c, KT_FLUX);
-    if (flux == SWE_HLL) launch_flux_ws<FLUX_HLL>(c, m, s, ws); else launch_flux_ws<FLUX_HLLC>(c, m, s, ws);
+    const bool opt = c->opt_roe_fix || c->opt_cfl_abs;  // the default instantiation is upstream as written
+    if (flux == SWE_HLL) { if (opt) launch_flux_ws<FLUX_HLL, true>(c, m, s, ws); else launch_flux_ws<FLUX_HLL, false>(c, m, s, ws); }
+    else { if (opt) launch_flux_ws<FLUX_HLLC, true>(c, m, s, ws); else launch_flux_ws<FLUX_HLLC, false>(c, m, s, ws); }
     kt_end(c, kt);
     return launch_check(c, "k_flux");
 }

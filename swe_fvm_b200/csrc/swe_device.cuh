@@ -94,12 +94,14 @@ __device__ __forceinline__ void gradient3(double x0, double y0, double z0, doubl
 }
 
 // ReconstructPartWetCell1 (src/MUSCLObject.cpp:86-112): flat free surface holding the cell volume.
-__device__ __noinline__ double partwet1_level(double w, double cb, double b13, double b23) {
+// *branch (optional): 0 submerged, 1 closed form (cbrt), 2 cubic by bisection.
+__device__ __noinline__ double partwet1_level(double w, double cb, double b13, double b23, int *branch) {
     double b12 = 3. * cb - b23 - b13;
     double b_delimiter = b12 + (1. / 3.) * (b13 - b12) * (b13 - b12) / (b13 - b23);
     double hi = w - cb;
-    if (w >= b13) return w;
-    if (w <= b_delimiter) return b23 + det_cbrt(3. * hi * (b13 - b23) * (b12 - b23));
+    if (w >= b13) { if (branch) *branch = 0; return w; }
+    if (w <= b_delimiter) { if (branch) *branch = 1; return b23 + det_cbrt(3. * hi * (b13 - b23) * (b12 - b23)); }
+    if (branch) *branch = 2;
     CubicPoly p;
     p.b = -3. * b13;
     p.c = 3. * (b12 * b13 + b13 * b23 - b12 * b23);
@@ -123,8 +125,9 @@ enum { WS_RUSANOV = 0, WS_DAVIS = 1, WS_EINFELDT = 2 };
 enum { FLUX_HLL = 0, FLUX_HLLC = 1 };
 
 // Wavespeeds (src/Fluxes.cpp:5-26). Einfeldt keeps `cl * ur` as written upstream (S5).
-template <int WS>
-__device__ __forceinline__ void wavespeeds(double ul, double hl, double ur, double hr, double &a0, double &a1) {
+// roe_fix (S5 alternative, only read when OPT): cr * ur instead of the as-written cl * ur.
+template <int WS, bool OPT = false>
+__device__ __forceinline__ void wavespeeds(double ul, double hl, double ur, double hr, double &a0, double &a1, int roe_fix = 0) {
     double cl = sqrt(hl), cr = sqrt(hr);
     if (WS == WS_RUSANOV) {
         double aplus = smax(fabs(ul) + cl, fabs(ur) + cr);
@@ -132,7 +135,7 @@ __device__ __forceinline__ void wavespeeds(double ul, double hl, double ur, doub
     } else if (WS == WS_DAVIS) {
         a0 = smin(ul - cl, ur - cr); a1 = smax(ul + cl, ur + cr);
     } else {
-        double uRoe = (cl * ul + cl * ur) / (cl + cr);
+        double uRoe = (cl * ul + ((OPT && roe_fix) ? cr : cl) * ur) / (cl + cr);
         double cRoe = sqrt(0.5 * (hl + hr));
         a0 = smin(ul - cl, uRoe - cRoe); a1 = smax(ur + cr, uRoe + cRoe);
     }
@@ -141,17 +144,18 @@ __device__ __forceinline__ void wavespeeds(double ul, double hl, double ur, doub
 // Fluxes::HLL<W> (include/Fluxes.h:14-54) / Fluxes::HLLC<W> (:56-111) on one interior edge.
 // (nx, ny) = outward normal of the `from` cell; t = (-ny, nx). l2w = length/wavespeed candidate
 // for the CFL min (left untouched on the early-outs, like the reference).
-template <int FLUX, int WS>
+// OPT: the S5 / S6 alternatives (roe_fix, cfl_abs) are honoured; the default instantiation is as written upstream.
+template <int FLUX, int WS, bool OPT = false>
 __device__ __forceinline__ void riemann_flux(double nx, double ny, double hl, double uxl, double uyl, double hr,
                                              double uxr, double uyr, double dmin, double abscor, double &f0,
-                                             double &f1, double &f2, double &l2w) {
+                                             double &f1, double &f2, double &l2w, int roe_fix = 0, int cfl_abs = 0) {
     const double tx = -ny, ty = nx;
     double ul = uxl * nx + uyl * ny;
     double ur = uxr * nx + uyr * ny;
     f0 = 0.; f1 = 0.; f2 = 0.;
     if (hl + hr <= 1e-10) return;
     double al, ar;
-    wavespeeds<WS>(ul, hl, ur, hr, al, ar);
+    wavespeeds<WS, OPT>(ul, hl, ur, hr, al, ar, roe_fix);
     const double Ul0 = hl, Ul1 = hl * uxl, Ul2 = hl * uyl;
     const double Ur0 = hr, Ur1 = hr * uxr, Ur2 = hr * uyr;
     if (FLUX == FLUX_HLL) {
@@ -171,7 +175,10 @@ __device__ __forceinline__ void riemann_flux(double nx, double ny, double hl, do
     double vr = uxr * tx + uyr * ty;
     double ustar = (ar - ur) * hr * ur - (al - ul) * hl * ul + 0.5 * (hl * hl - hr * hr);
     ustar /= (hr * (ar - ur) - hl * (al - ul));
-    l2w = dmin / (abscor + smax(kTol, smax(al, ar)));  // S6: signed max as written
+    {   // S6: signed max as written; cfl_abs: magnitudes
+        const double amax = (OPT && cfl_abs) ? smax(fabs(al), fabs(ar)) : smax(al, ar);
+        l2w = dmin / (abscor + smax(kTol, amax));
+    }
     if (ustar <= 0) {
         double urstar = vr * tx + ustar * ty;
         double vrstar = vr * nx + ustar * ny;

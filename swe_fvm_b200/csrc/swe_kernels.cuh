@@ -48,7 +48,16 @@ struct DevFields {
     double *scal;                    // [0] min_len_to_wavespeed, [1] dt, [2] time, [3] running min
     int *flags;                      // [0] non-finite state seen, [1] part-wet list count, [3] flux block ticket,
                                      // [4] generic-reconstruction list count, [5] peer-memory wait timed out
+    unsigned long long *dbg;         // [12] branch-hit counters (TAPS builds only; see swe_get_branch_counts)
+    int recon;                       // S2: 0 repaired (w,u,v plane gradients), 1 as written upstream, 2 first order
+    int pw2;                         // S3: 0 PartWet2 points(r,c) read as (point, coordinate), 1 as written
 };
+// branch-hit counter slots (same meaning as oracle/swe_oracle.cpp `branch`)
+enum { BR_PW1_SUBMERGED = 0, BR_PW1_CBRT, BR_PW1_BISECTION, BR_FW_DRY_NB, BR_FW_PW_NB, BR_FW_VERTEX_ZERO, BR_FW_TVD_OFF,
+       BR_PW2_TO_PW1, BR_PW2_ONE_WET, BR_PW2_THREE_WET, BR_PW2_TWO_WET, BR_PW2_FALLBACK, BR_COUNT };
+template <bool TAPS> __device__ __forceinline__ void count_branch(const DevFields &s, int b) {
+    if (TAPS) atomicAdd(&s.dbg[b], 1ull);
+}
 
 constexpr int kBlock = 128;
 
@@ -158,38 +167,45 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
         gradient3(P0.x, P0.y, P0.z, P1.x, P1.y, P1.z, P2.x, P2.y, P2.z, M.g00, M.g01);
     } else if (!full) {  // ReconstructPartWetCell1 (:86-112)
         const double bmin = smin(smin(P0.z, P1.z), P2.z);
-        M.o0 = partwet1_level(w, cb, bmax, bmin); M.o1 = u; M.o2 = v;
+        int br = 0;
+        M.o0 = partwet1_level(w, cb, bmax, bmin, &br); M.o1 = u; M.o2 = v;
+        count_branch<TAPS>(s, BR_PW1_SUBMERGED + br);
         s.pw_list[atomicAdd(&s.flags[1], 1)] = i;
     } else {  // ReconstructFullWetCell (:38-84), S2: plane gradients of w, u, v
         M.o0 = w; M.o1 = u; M.o2 = v;
-        double X[3][2], V[3][3];
-        bool zero_grad = false;
+        double X[3][2], V[3][3], Z[3];  // Z: bed of the support point (the as-written w-gradient uses it)
+        bool zero_grad = false, pw_nb = false;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int j = jt[k];
             const double wj = N[k][0], uj = N[k][1], vj = N[k][2];
             const double4 Gj = Gn[k];
             if (Gj.w < wj) {  // IsFullWetCell(j): bfull = +inf on boundary triangles
-                X[k][0] = Gj.x; X[k][1] = Gj.y;
+                X[k][0] = Gj.x; X[k][1] = Gj.y; Z[k] = Gj.z;
                 V[k][0] = wj; V[k][1] = uj; V[k][2] = vj;
             } else if (!is_wet(wj - Gj.z)) {  // IsDryCell(j) -> zero gradient
                 zero_grad = true;
-                X[k][0] = X[k][1] = 0.; V[k][0] = V[k][1] = V[k][2] = 0.;
+                X[k][0] = X[k][1] = 0.; Z[k] = 0.; V[k][0] = V[k][1] = V[k][2] = 0.;
             } else {  // part-wet neighbour (rare): its PartWet1 value at the shared edge midpoint
+                if (!zero_grad) pw_nb = true;  // upstream returns at the first dry neighbour (:52-53)
                 const double z0 = m.node[m.tp[j]].z, z1 = m.node[m.tp[nt + j]].z, z2 = m.node[m.tp[2 * nt + j]].z;
                 const double b13 = smax(smax(z0, z1), z2), b23 = smin(smin(z0, z1), z2);
-                double a0 = partwet1_level(wj, Gj.z, b13, b23), a1 = uj, a2 = vj;
+                double a0 = partwet1_level(wj, Gj.z, b13, b23, nullptr), a1 = uj, a2 = vj;
                 // AtPoint with a zero gradient: o + (0*dx + 0*dy)
                 const double dx = mxk[k] - Gj.x, dy = myk[k] - Gj.y;
                 a0 = a0 + (0. * dx + 0. * dy); a1 = a1 + (0. * dx + 0. * dy); a2 = a2 + (0. * dx + 0. * dy);
                 if (!((a0 - mbk[k]) >= 0)) { a0 = mbk[k]; a1 = 0.; a2 = 0.; }
-                X[k][0] = mxk[k]; X[k][1] = myk[k];
+                X[k][0] = mxk[k]; X[k][1] = myk[k]; Z[k] = mbk[k];
                 V[k][0] = 0.5 * (w + a0); V[k][1] = 0.5 * (u + a1); V[k][2] = 0.5 * (v + a2);
             }
         }
-        if (!zero_grad) {
+        if (zero_grad) count_branch<TAPS>(s, BR_FW_DRY_NB);
+        if (pw_nb) count_branch<TAPS>(s, BR_FW_PW_NB);
+        if (!zero_grad && s.recon != 2) {  // recon == 2: first order, the gradient stays zero
             const Lu2 lu = lu2_factor(X[0][0], X[0][1], X[1][0], X[1][1], X[2][0], X[2][1]);
             double df[3][2];
+            const bool asw = s.recon == 1;  // as written (:63-64): df.row(0) = Gradient(grad_points), u/v rows zero
+            if (asw) { V[0][0] = Z[0]; V[1][0] = Z[1]; V[2][0] = Z[2]; }
             lu2_solve(lu, V[0][0], V[1][0], V[2][0], df[0][0], df[0][1]);
             // vertex positivity (:66-72): dx = P(ip) * (I - 1/3), evaluated literally
             const double md = 1. - 1. / 3., mo = 0. - 1. / 3.;
@@ -202,7 +218,9 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
             const bool positive = is_wet(hp0) && is_wet(hp1) && is_wet(hp2);
             lu2_solve(lu, V[0][1], V[1][1], V[2][1], df[1][0], df[1][1]);
             lu2_solve(lu, V[0][2], V[1][2], V[2][2], df[2][0], df[2][1]);
+            if (asw) df[1][0] = df[1][1] = df[2][0] = df[2][1] = 0.;
             if (!positive) {
+                count_branch<TAPS>(s, BR_FW_VERTEX_ZERO);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) df[c][0] = df[c][1] = 0.;
             }
@@ -219,6 +237,7 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
                     if (!((lo <= vek) && (vek <= hi))) tvd[c] = 0.;
                 }
             }
+            if (tvd[0] == 0. || tvd[1] == 0. || tvd[2] == 0.) count_branch<TAPS>(s, BR_FW_TVD_OFF);
             M.g00 = tvd[0] * df[0][0]; M.g01 = tvd[0] * df[0][1];
             M.g10 = tvd[1] * df[1][0]; M.g11 = tvd[1] * df[1][1];
             M.g20 = tvd[2] * df[2][0]; M.g21 = tvd[2] * df[2][1];
@@ -239,11 +258,19 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
 #ifndef SWE_K1_SPLIT
 #define SWE_K1_SPLIT 1
 #endif
-template <bool TAPS>
+// arithmetic of the fast path on already loaded data (shared by the gather kernel and the tiled kernel)
+template <bool TAPS, int RECON>
+__device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, const int i, const bool bnd, const double4 P0,
+                                             const double4 P1, const double4 P2, const double4 Gi, const double w,
+                                             const double u, const double v, const double N00, const double N01,
+                                             const double N02, const double N10, const double N11, const double N12,
+                                             const double N20, const double N21, const double N22, const double4 G0,
+                                             const double4 G1, const double4 G2);
+
+template <bool TAPS, int RECON>
 __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const DevFields &s, const int i, const int ip0,
                                                       const int ip1, const int ip2, const int it0, const int it1,
                                                       const int it2) {
-    const int nt = m.nt;
     const int j0 = max(it0, 0), j1 = max(it1, 0), j2 = max(it2, 0);
     const double4 P0 = ldg4(m.node + ip0), P1 = ldg4(m.node + ip1), P2 = ldg4(m.node + ip2);
     const double4 Gi = ldg4(m.cgeo + i);
@@ -252,8 +279,18 @@ __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const De
     const double N10 = __ldg(s.w + j1), N11 = __ldg(s.u + j1), N12 = __ldg(s.v + j1);
     const double N20 = __ldg(s.w + j2), N21 = __ldg(s.u + j2), N22 = __ldg(s.v + j2);
     const double4 G0 = ldg4(m.cgeo + j0), G1 = ldg4(m.cgeo + j1), G2 = ldg4(m.cgeo + j2);
+    return fast_compute<TAPS, RECON>(s, m.nt, i, (it0 | it1 | it2) < 0, P0, P1, P2, Gi, w, u, v, N00, N01, N02, N10, N11, N12,
+                                     N20, N21, N22, G0, G1, G2);
+}
+
+template <bool TAPS, int RECON>
+__device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, const int i, const bool bnd, const double4 P0,
+                                             const double4 P1, const double4 P2, const double4 Gi, const double w,
+                                             const double u, const double v, const double N00, const double N01,
+                                             const double N02, const double N10, const double N11, const double N12,
+                                             const double N20, const double N21, const double N22, const double4 G0,
+                                             const double4 G1, const double4 G2) {
     const double cx = Gi.x, cy = Gi.y, cb = Gi.z;
-    const bool bnd = (it0 | it1 | it2) < 0;
     const bool dry = !is_wet(w - cb);
     const bool full = !bnd && (smax(smax(P0.z, P1.z), P2.z) < w);
     const bool nbfull = (G0.w < N00) && (G1.w < N10) && (G2.w < N20);
@@ -268,11 +305,16 @@ __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const De
     if (dry) {  // ReconstructDryCell (src/MUSCLObject.cpp:31-36)
         M.o0 = cb; M.o1 = 0.; M.o2 = 0.;
         gradient3(P0.x, P0.y, P0.z, P1.x, P1.y, P1.z, P2.x, P2.y, P2.z, M.g00, M.g01);
+    } else if (RECON == 2) {  // first-order option: MUSCL{prim(i), 0}
+        M.o0 = w; M.o1 = u; M.o2 = v;
     } else {  // ReconstructFullWetCell (:38-84) with three full-wet neighbours
         M.o0 = w; M.o1 = u; M.o2 = v;
         const Lu2 lu = lu2_factor(G0.x, G0.y, G1.x, G1.y, G2.x, G2.y);
         double d00, d01, d10, d11, d20, d21;
-        lu2_solve(lu, N00, N10, N20, d00, d01);
+        // RECON 1 = as written upstream (:63-64): the w-gradient is the slope of the BED values of the
+        // support points (Gradient(grad_points)), the u and v rows stay zero
+        if (RECON == 1) lu2_solve(lu, G0.z, G1.z, G2.z, d00, d01);
+        else lu2_solve(lu, N00, N10, N20, d00, d01);
         const double md = 1. - 1. / 3., mo = 0. - 1. / 3.;
         const double dx0 = (P0.x * md + P1.x * mo) + P2.x * mo, dy0 = (P0.y * md + P1.y * mo) + P2.y * mo;
         const double dx1 = (P0.x * mo + P1.x * md) + P2.x * mo, dy1 = (P0.y * mo + P1.y * md) + P2.y * mo;
@@ -281,9 +323,12 @@ __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const De
         const double hp1 = ((d00 * dx1 + d01 * dy1) + w) - P1.z;
         const double hp2 = ((d00 * dx2 + d01 * dy2) + w) - P2.z;
         const bool positive = is_wet(hp0) && is_wet(hp1) && is_wet(hp2);
-        lu2_solve(lu, N01, N11, N21, d10, d11);
-        lu2_solve(lu, N02, N12, N22, d20, d21);
-        if (!positive) { d00 = d01 = d10 = d11 = d20 = d21 = 0.; }
+        if (RECON == 1) { d10 = d11 = d20 = d21 = 0.; }
+        else {
+            lu2_solve(lu, N01, N11, N21, d10, d11);
+            lu2_solve(lu, N02, N12, N22, d20, d21);
+        }
+        if (!positive) { count_branch<TAPS>(s, BR_FW_VERTEX_ZERO); d00 = d01 = d10 = d11 = d20 = d21 = 0.; }
         // on/off TVD limiter (:74-81): lo <= v_e <= hi with lo/hi = min/max of the two cell means
         const double ex0 = mx0 - cx, ey0 = my0 - cy, ex1 = mx1 - cx, ey1 = my1 - cy, ex2 = mx2 - cx, ey2 = my2 - cy;
         double t0 = 1., t1 = 1., t2 = 1.;
@@ -299,6 +344,7 @@ __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const De
         SWE_TVD(t0, w, N10, d00, d01, ex1, ey1) SWE_TVD(t1, u, N11, d10, d11, ex1, ey1) SWE_TVD(t2, v, N12, d20, d21, ex1, ey1)
         SWE_TVD(t0, w, N20, d00, d01, ex2, ey2) SWE_TVD(t1, u, N21, d10, d11, ex2, ey2) SWE_TVD(t2, v, N22, d20, d21, ex2, ey2)
 #undef SWE_TVD
+        if (TAPS && (t0 == 0. || t1 == 0. || t2 == 0.)) count_branch<TAPS>(s, BR_FW_TVD_OFF);
         M.g00 = t0 * d00; M.g01 = t0 * d01;
         M.g10 = t1 * d10; M.g11 = t1 * d11;
         M.g20 = t2 * d20; M.g21 = t2 * d21;
@@ -323,7 +369,7 @@ __global__ void __launch_bounds__(kBlock) k_reconstruct_slow(DevMesh m, DevField
 
 // persistent grid-stride kernel over the cell range [first, last); the ids of the thread's next
 // cell are fetched before the current cell is processed (hides the first memory round trip)
-template <bool TAPS>
+template <bool TAPS, int RECON>
 __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s, int first, int last) {
     const int nt = m.nt;
     const int stride = gridDim.x * blockDim.x;
@@ -339,12 +385,132 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(Dev
             nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
         }
 #if SWE_K1_SPLIT
-        if (!reconstruct_cell_fast<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
+        if (!reconstruct_cell_fast<TAPS, RECON>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
 #else
         reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
 #endif
         if (nx >= last) break;
         i = nx; ip0 = np0; ip1 = np1; ip2 = np2; it0 = nt0; it1 = nt1; it2 = nt2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1, tiled form (SWE_K1_TILED, the default): the block's cell patch is staged in shared memory.
+// Cells are numbered along a Hilbert curve, so a tile of kTile consecutive cells is a compact patch
+// and ~94-96 % of its neighbour references fall inside the tile itself (measured on the structured
+// and the Gmsh meshes). Per tile one thread issues 1-D TMA bulk copies (cp.async.bulk -> mbarrier
+// complete_tx) of the tile's CONTIGUOUS ranges of tp/tt ids, w/u/v and the cgeo packets into a
+// double-buffered stage; the copies of tile n+1 fly while tile n is computed. Neighbour data is then
+// read from shared memory (LDS) when the neighbour lies in the tile and gathered from global memory
+// otherwise; only the node packets are always gathered (they are shared by ~6 cells and hit L1).
+// Partial tiles at the ends of a cell range use plain guarded loads into the same stage.
+// ---------------------------------------------------------------------------------------
+#ifndef SWE_K1_TILED
+#define SWE_K1_TILED 1
+#endif
+#ifndef SWE_K1_TILE
+#define SWE_K1_TILE 128
+#endif
+constexpr int kTile = SWE_K1_TILE;
+struct __align__(128) K1Stage {
+    double4 cgeo[kTile];
+    double w[kTile], u[kTile], v[kTile];
+    int tp[3][kTile], tt[3][kTile];
+};
+constexpr unsigned kK1StageBytes = kTile * (32 + 24 + 24);
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(phase)
+                     : "memory");
+    } while (!ok);
+}
+
+// issue the copies of tile [base, base + kTile) (must be a full, aligned tile) into stage st
+__device__ __forceinline__ void k1_stage_issue(const DevMesh &m, const DevFields &s, K1Stage &st, unsigned long long *bar, int base) {
+    const int nt = m.nt;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage are done
+    mbar_expect_tx(bar, kK1StageBytes);
+    tma_load_1d(st.cgeo, m.cgeo + base, kTile * 32, bar);
+    tma_load_1d(st.w, s.w + base, kTile * 8, bar);
+    tma_load_1d(st.u, s.u + base, kTile * 8, bar);
+    tma_load_1d(st.v, s.v + base, kTile * 8, bar);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        tma_load_1d(st.tp[k], m.tp + (size_t)k * nt + base, kTile * 4, bar);
+        tma_load_1d(st.tt[k], m.tt + (size_t)k * nt + base, kTile * 4, bar);
+    }
+}
+
+template <bool TAPS, int RECON>
+__global__ void __launch_bounds__(kTile, SWE_K1_MIN_BLOCKS) k_reconstruct_tiled(DevMesh m, DevFields s, int first, int last) {
+    __shared__ K1Stage stage[2];
+    __shared__ unsigned long long bar[2];
+    const int nt = m.nt;
+    const int tid = threadIdx.x;
+    const int tile0 = first / kTile, tile1 = (last + kTile - 1) / kTile;  // tiles on absolute kTile boundaries
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    // a tile can be fetched by TMA when it lies entirely inside [first, last) and nt keeps the k-major id rows 16-byte aligned
+    const bool rows_aligned = (nt & 3) == 0;
+    auto full = [&](int t) { return rows_aligned && t * kTile >= first && (t + 1) * kTile <= last; };
+    unsigned phase[2] = {0u, 0u};
+    int t = tile0 + blockIdx.x;
+    if (t < tile1 && full(t) && tid == 0) k1_stage_issue(m, s, stage[0], &bar[0], t * kTile);
+    int b = 0;
+    for (; t < tile1; t += gridDim.x, b ^= 1) {
+        const int base = t * kTile;
+        const int tn = t + gridDim.x;
+        if (tn < tile1 && full(tn) && tid == 0) k1_stage_issue(m, s, stage[b ^ 1], &bar[b ^ 1], tn * kTile);
+        K1Stage &st = stage[b];
+        const int i = base + tid;
+        const bool active = i >= first && i < last;
+        if (full(t)) {
+            mbar_wait(&bar[b], phase[b]);
+            phase[b] ^= 1u;
+        } else {  // partial tile: guarded loads
+            if (active) {
+                st.cgeo[tid] = ldg4(m.cgeo + i);
+                st.w[tid] = s.w[i]; st.u[tid] = s.u[i]; st.v[tid] = s.v[i];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { st.tp[k][tid] = m.tp[(size_t)k * nt + i]; st.tt[k][tid] = m.tt[(size_t)k * nt + i]; }
+            }
+            __syncthreads();
+        }
+        if (active) {
+            const int lo = max(base, first), hi = min(base + kTile, last);  // staged range of this tile
+            const int ip0 = st.tp[0][tid], ip1 = st.tp[1][tid], ip2 = st.tp[2][tid];
+            const int it0 = st.tt[0][tid], it1 = st.tt[1][tid], it2 = st.tt[2][tid];
+            const double4 P0 = ldg4(m.node + ip0), P1 = ldg4(m.node + ip1), P2 = ldg4(m.node + ip2);
+            // boundary sides point at the cell itself (values unused); in-tile neighbours come from the stage
+            const int j0 = it0 < 0 ? i : it0, j1 = it1 < 0 ? i : it1, j2 = it2 < 0 ? i : it2;
+            double N00, N01, N02, N10, N11, N12, N20, N21, N22;
+            double4 G0, G1, G2;
+#define SWE_NB(J, A, B, C, G)                                                           \
+            if (J >= lo && J < hi) { const int q = J - base; A = st.w[q]; B = st.u[q]; C = st.v[q]; G = st.cgeo[q]; } \
+            else { A = __ldg(s.w + J); B = __ldg(s.u + J); C = __ldg(s.v + J); G = ldg4(m.cgeo + J); }
+            SWE_NB(j0, N00, N01, N02, G0) SWE_NB(j1, N10, N11, N12, G1) SWE_NB(j2, N20, N21, N22, G2)
+#undef SWE_NB
+            if (!fast_compute<TAPS, RECON>(s, nt, i, (it0 | it1 | it2) < 0, P0, P1, P2, st.cgeo[tid], st.w[tid], st.u[tid], st.v[tid],
+                                           N00, N01, N02, N10, N11, N12, N20, N21, N22, G0, G1, G2))
+                s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
+        }
+        __syncthreads();  // every thread is done with stage b before it is refilled two tiles later
     }
 }
 
@@ -357,7 +523,7 @@ __device__ __noinline__ double pass1_w_at_node(const DevMesh &m, const DevFields
     double o0, g0, g1;
     if (c == 1) {  // PartWet1: flat level, zero gradient (its cgx/cgy may already hold pass-2 values)
         const double z0 = m.node[m.tp[t]].z, z1 = m.node[m.tp[nt + t]].z, z2 = m.node[m.tp[2 * nt + t]].z;
-        o0 = partwet1_level(s.w[t], G.z, smax(smax(z0, z1), z2), smin(smin(z0, z1), z2));
+        o0 = partwet1_level(s.w[t], G.z, smax(smax(z0, z1), z2), smin(smin(z0, z1), z2), nullptr);
         g0 = 0.; g1 = 0.;
     } else {
         o0 = (c == 0) ? G.z : s.w[t];
@@ -398,7 +564,7 @@ __global__ void __launch_bounds__(kBlock) k_partwet2(DevMesh m, DevFields s) {
         if (Q1.z > Q2.z) { double4 t = Q1; Q1 = Q2; Q2 = t; int ti = q1; q1 = q2; q2 = ti; }
         if (Q0.z > Q1.z) { double4 t = Q0; Q0 = Q1; Q1 = t; int ti = q0; q0 = q1; q1 = ti; }
         const double b23 = Q0.z, b12 = Q1.z, b13 = Q2.z;
-        if ((w > b13) || (b13 - b23 < kTol)) continue;  // falls back to PartWet1 = what pass 1 wrote
+        if ((w > b13) || (b13 - b23 < kTol)) { count_branch<TAPS>(s, BR_PW2_TO_PW1); continue; }  // PartWet1 = what pass 1 wrote
 
         const double w23 = node_max_w(m, s, q0, Q0.x, Q0.y, Q0.z);
         const double h23 = w23 - b23;
@@ -407,18 +573,25 @@ __global__ void __launch_bounds__(kBlock) k_partwet2(DevMesh m, DevFields s) {
         const double h_delimiter2 = 1. / 3. * h23 * (2. * b13 - b12 - b23) / (b13 - b23);
         const double hi = w - cb;
         const double ratio_h = hi / h23;
-        const double S0x = Q0.x, S0y = Q0.y, S0z = w23;
+        // as written (s.pw2 == 1, :143,158-159,180) the scalar accesses points(0,2) / points(1,2) land on entries
+        // that points.col(2) = ... overwrites afterwards: S0.z stays b23 and S1.z stays b12
+        const bool asw = s.pw2 != 0;
+        const double S0x = Q0.x, S0y = Q0.y, S0z = asw ? Q0.z : w23;
         double S1x, S1y, S1z, S2x, S2y, S2z;
         if (hi <= h_delimiter1) {  // one vertex wet
+            count_branch<TAPS>(s, BR_PW2_ONE_WET);
             const double k2 = sqrt(3. * ratio_h / ratio_b);
             S1x = k2 * Q1.x + (1. - k2) * Q0.x; S1y = k2 * Q1.y + (1. - k2) * Q0.y; S1z = k2 * Q1.z + (1. - k2) * Q0.z;
             const double k3 = sqrt(3. * ratio_h * ratio_b);
             S2x = k3 * Q2.x + (1. - k3) * Q0.x; S2y = k3 * Q2.y + (1. - k3) * Q0.y; S2z = k3 * Q2.z + (1. - k3) * Q0.z;
         } else if (hi >= h_delimiter2) {  // three vertices wet
+            count_branch<TAPS>(s, BR_PW2_THREE_WET);
             const double delta_w = 1.5 * (hi - h_delimiter2);
             S1x = Q1.x; S1y = Q1.y; S1z = Q1.z;
-            S1z += delta_w;
-            S1z += (1. - ratio_b) * h23;
+            if (!asw) {
+                S1z += delta_w;
+                S1z += (1. - ratio_b) * h23;
+            }
             S2x = Q2.x; S2y = Q2.y; S2z = Q2.z;
             S2z += delta_w;
         } else {  // two vertices wet
@@ -427,11 +600,12 @@ __global__ void __launch_bounds__(kBlock) k_partwet2(DevMesh m, DevFields s) {
             CubicPoly p;
             p.d = (1. + beta - alpha) / (beta * beta); p.c = (alpha - 3.) / beta; p.b = 0.;
             const double k1 = 1. - bisection(p, 0., 1.);
-            if (k1 < kTol) continue;
+            if (k1 < kTol) { count_branch<TAPS>(s, BR_PW2_FALLBACK); continue; }
+            count_branch<TAPS>(s, BR_PW2_TWO_WET);
             const double k3 = 1. - beta * (1. - k1);
             const double bp1 = k1 * b13 + (1. - k1) * b12;
             S1x = Q1.x; S1y = Q1.y;
-            S1z = b12 + (k1 / k3) * beta * h23;
+            S1z = asw ? Q1.z : b12 + (k1 / k3) * beta * h23;
             S2x = k1 * Q2.x + (1. - k1) * Q1.x;
             S2y = k1 * Q2.y + (1. - k1) * Q1.y;
             S2z = bp1;
@@ -474,8 +648,8 @@ __device__ __forceinline__ double warp_min(double v) {
 #ifndef SWE_K2_MIN_BLOCKS
 #define SWE_K2_MIN_BLOCKS 8
 #endif
-template <int FLUX, int WS>
-__global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, DevFields s, double abscor) {
+template <int FLUX, int WS, bool OPT>
+__global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, DevFields s, double abscor, int roe_fix, int cfl_abs) {
     const int ne = m.ne;
     const int stride = gridDim.x * blockDim.x;
     double l2w = 1.0;  // reset value of m_min_length_to_wavespeed (:56)
@@ -494,8 +668,9 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
                 elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
             } else {
                 double cand = 1.0;
-                riemann_flux<FLUX, WS>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
-                                       __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand);
+                riemann_flux<FLUX, WS, OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
+                                            __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand,
+                                            roe_fix, cfl_abs);
                 l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
             }
             st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);

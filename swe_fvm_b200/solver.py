@@ -110,6 +110,24 @@ class SpaceDisc:
     def cell_class(self) -> np.ndarray:
         return self._get("swe_get_cell_class", (self.nt,), dtype=np.int8)
 
+    BRANCHES = ("pw1_submerged", "pw1_cbrt", "pw1_bisection", "fw_dry_neighbour", "fw_partwet_neighbour", "fw_vertex_zeroed",
+                "fw_tvd_off", "pw2_to_pw1", "pw2_one_wet", "pw2_three_wet", "pw2_two_wet", "pw2_two_wet_fallback")
+
+    def set_option(self, key: str, value: int):
+        """Semantic-decision switches: recon (0 repaired | 1 as written | 2 first order), pw2, roe_fix, cfl_abs."""
+        self._call("swe_set_option", key.encode(), int(value))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int32()
+        self._call("swe_get_option", key.encode(), C.byref(v))
+        return v.value
+
+    def branch_counts(self) -> dict:
+        """How many cells took each reconstruction branch in the last ComputeInterfaceValues (taps on)."""
+        out = np.zeros(12, dtype=np.int64)
+        self._call("swe_get_branch_counts", out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return dict(zip(self.BRANCHES, out.tolist()))
+
     def diagnostics(self) -> dict:
         out = self._get("swe_diagnostics", (6,))
         return dict(mass=out[0], kinetic=out[1], potential=out[2], vmax=out[3], hmin=out[4], wet_cells=int(out[5]))

@@ -91,6 +91,122 @@ def test_step_parity_all_schemes_fluxes(cases, scheme, flux, ws):
     assert td.CFLdt() == ref.cfl_dt()
 
 
+def _front_states(mesh, v0):
+    from conftest import crafted_branch_state, random_front_state
+    T = mesh.centroids()
+    yield "ic", v0
+    for seed, level in ((0, -0.6), (1, -0.3), (2, 0.0), (3, 7.5)):
+        yield f"rough{seed}", random_front_state(mesh, T, seed, level)
+    yield "crafted", crafted_branch_state(mesh, T)
+
+
+def _rough_bed_case():
+    from swe_fvm_b200 import StructTriangMesh
+    m2 = StructTriangMesh(16, 16, 0.25)
+    rng = np.random.default_rng(11)
+    m2.geometry[:, 2] = 0.05 * rng.standard_normal(m2.nn)
+    b13 = m2.geometry[:, 2][m2.element_nodes].max(1)
+    return m2, np.stack([b13 + 10.0 ** rng.uniform(-6, -1, m2.nt), 0.1 * rng.standard_normal(m2.nt), 0.1 * rng.standard_normal(m2.nt)], 1)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(recon=1, pw2=1), dict(recon=2), dict(recon=1), dict(pw2=1),
+                                  dict(roe_fix=1, cfl_abs=1), dict(recon=1, pw2=1, roe_fix=1)])
+@pytest.mark.parametrize("reorder", [False, True])
+def test_semantic_switches_and_every_branch_bit_exact(opts, reorder):
+    """swe_set_option(recon / pw2 / roe_fix / cfl_abs) against the oracle with the same switches (the oracle's
+    as-written mode equals upstream's own sources bit for bit, tests/test_ref_anchor.py), on states that
+    drive the reconstruction through EVERY branch of ReconstructPartWetCell1/2 and ReconstructFullWetCell;
+    the device's branch-hit counters must equal the oracle's."""
+    from oracle.oracle import Oracle
+    from swe_fvm_b200.solver import SpaceDisc
+    mesh0, case, v0 = make_case("classic_thacker", 24)
+    total = np.zeros(12, dtype=np.int64)
+    work = [(mesh0, n, st) for n, st in _front_states(mesh0, v0)] + [(_rough_bed_case()[0], "film", _rough_bed_case()[1])]
+    for mesh, name, st in work:
+        sd = SpaceDisc("hllc", "einfeldt", mesh, st, cor=0.3, reorder=reorder, taps=True)
+        ref = Oracle(mesh, cor=0.3, **opts)
+        ref.set_state(st)
+        for k, v in opts.items():
+            sd.set_option(k, v)
+            assert sd.get_option(k) == v
+        sd.ComputeInterfaceValues()
+        ref.compute_interface_values()
+        np.testing.assert_array_equal(sd.cell_class(), ref.cell_class(), err_msg=name)
+        np.testing.assert_array_equal(sd.node_max_w(), ref.node_max_w(), err_msg=name)
+        np.testing.assert_array_equal(sd.GetEdgField(), ref.edge_states(), err_msg=name)
+        np.testing.assert_array_equal(sd.GetSrcField(), ref.sources(), err_msg=name)
+        assert sd.branch_counts() == ref.branch_counts(), name
+        total += np.array(list(sd.branch_counts().values()))
+        for fl, ws in ((1, 2), (0, 2), (1, 1)):
+            sd.flux, sd.wavespeed = fl, ws
+            sd.ComputeFluxes()
+            ref.compute_fluxes(fl, ws)
+            np.testing.assert_array_equal(sd.GetFluxes(), ref.fluxes(), err_msg=name)
+            assert sd.GetMinLenToWavespeed() == ref.min_len_to_wavespeed()
+        sd.flux, sd.wavespeed = 1, 2
+        for _ in range(4):  # whole steps from this state
+            sd._call("swe_step", 1, 1, 2, 2e-3)
+            ref.step(1, 1, 2, 2e-3)
+        np.testing.assert_array_equal(sd.GetVolField(), ref.get_state(), err_msg=name)
+        sd.close()
+    hit = dict(zip(SpaceDisc.BRANCHES, total.tolist()))
+    if opts.get("recon") == 2:  # first order: no gradient, so nothing for the vertex check / TVD test to switch off
+        hit.pop("fw_vertex_zeroed"), hit.pop("fw_tvd_off")
+    assert all(v > 0 for v in hit.values()), str(hit)
+
+
+def test_golden_step_out1_on_the_gpu():
+    """The one step for which upstream holds an output (notebooks/out1.dat: testGaussWave, Euler, HLL<Einfeldt>,
+    dt = 1e-3, examples/Main.cpp:172-195) on the GPU in as-written mode: within 5 % rel-L2 of the dump (it was
+    written by an intermediate revision), equal to the oracle's as-written mode bit for bit, and
+    equal to upstream's own sources compiled in oracle/_ref when that library travelled with the tree."""
+    import gzip
+    import os
+    from conftest import GOLDEN
+    from oracle.oracle import Oracle
+    from swe_fvm_b200 import TriangMesh
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    bowl = TriangMesh.from_gmsh(os.path.join(GOLDEN, "bowl.msh"))
+    mesh, case, v0 = make_case("gauss_wave", mesh=bowl)
+    out1 = np.loadtxt(gzip.open(os.path.join(GOLDEN, "out1.dat.gz"), "rt"))
+    sd = SpaceDisc("hll", "einfeldt", mesh, v0, reorder=True)
+    sd.set_option("recon", 1)
+    sd.set_option("pw2", 1)
+    Solvers.Euler(TimeDisc(sd), 1e-3)
+    q = sd.GetVolField()
+    hu, hv = q[:, 0] * q[:, 1], q[:, 0] * q[:, 2]
+    assert rel_l2(hu, out1[:, 1]) < 0.05 and rel_l2(hv, out1[:, 2]) < 0.05
+    assert rel_l2(q[:, 0], out1[:, 0]) < 1e-4
+    o = Oracle(mesh, recon=1, pw2=1)
+    o.set_state(v0)
+    o.step(0, 0, 2, 1e-3)
+    np.testing.assert_array_equal(q, o.get_state())
+    from oracle import ref
+    if os.path.exists(ref.lib_path("aswritten")):
+        r = ref.Ref(mesh, variant="aswritten")
+        r.set_state(v0)
+        r.step(0, 0, 2, 1e-3)
+        # upstream's in-place loops (S7/S8) are invisible on this fully wet flat-bed case
+        np.testing.assert_array_equal(q, r.get_state())
+
+
+def test_create_rejects_another_local_edge_order():
+    """swe_create validates the local convention the kernels rely on (edge k joins nodes k, k+1; neighbour k across it)."""
+    from swe_fvm_b200 import StructTriangMesh, SweError
+    from swe_fvm_b200.solver import SpaceDisc
+    mesh = StructTriangMesh(4, 4, 1.0)
+    good_e, good_t = mesh.element_edges.copy(), mesh.element_neighbours.copy()
+    mesh.element_edges[:] = np.roll(good_e, 1, axis=1)      # e.g. "edge k opposite node k"
+    mesh.element_neighbours[:] = np.roll(good_t, 1, axis=1)
+    with pytest.raises(SweError) as ei:
+        SpaceDisc("hllc", "einfeldt", mesh)
+    assert ei.value.status == -1 and "element_edges[k] must join" in str(ei.value)
+    mesh.element_edges[:] = good_e                           # edges right, neighbours rotated
+    with pytest.raises(SweError) as ei:
+        SpaceDisc("hllc", "einfeldt", mesh)
+    assert "element_neighbours[k] must be the cell across" in str(ei.value)
+
+
 def test_lake_at_rest_config0(cases):
     """configs[0]: LakeAtRest on StructTriangMesh(71,71,4/71), HLLC<Einfeldt>, Euler, dt=1e-3:
     velocities stay at machine zero, w stays 0."""
