@@ -270,6 +270,83 @@ SWE_API const int32_t *swe_hostmesh_cell_owner(const swe_hostmesh *m);   /* nt, 
 SWE_API int swe_partition_rcb(const swe_hostmesh *m, int32_t nparts, int32_t *part_nt);
 
 /* ------------------------------------------------------------------------------------ */
+/* Multi-GPU time step behind the C-ABI: decomposition plan (host) + distributed context    */
+/* ------------------------------------------------------------------------------------ */
+/* The reference steps one SpaceDisc with Solvers::X(TimeDisc*, dt) (include/Solvers.h:6-8); swe_dist_step /
+ * swe_dist_run are the same call on N GPUs. Everything multi-GPU lives below this boundary: the
+ * decomposition (strips of a StructTriangMesh, or any mesh + partition vector), the per-rank device
+ * contexts with halo cells, the peer-memory halo exchange fused into the stage (pack-and-signal right
+ * after the boundary cells are updated, wait-and-unpack before the halo-dependent reconstruction), and
+ * the global CFL minimum over peer memory. A launcher only provides ONE bootstrap primitive, an
+ * all-gather of a small fixed-size blob (swe_allgather_fn), used during creation to exchange CUDA-IPC
+ * handles; no launcher code runs on the data path. One process per GPU (swe_dist_create_*) or one
+ * process driving several GPUs (swe_dist_group_create_*, no bootstrap needed). Results on owned cells
+ * are bit-identical to the single-GPU run for any GPU count. */
+typedef struct swe_dist_plan swe_dist_plan; /* host only: who owns what, halo lists (no GPU needed)      */
+typedef struct swe_dist swe_dist;           /* one rank: plan + device context + peer mappings           */
+
+/* rank r owns an even share of the nj rows of squares of StructTriangMesh(ni, nj, h) plus 3 halo rows per
+ * open side; the local block is generated directly (no global mesh in memory). */
+SWE_API int swe_dist_plan_struct(swe_dist_plan **out, int32_t rank, int32_t world, int64_t ni, int64_t nj, double h);
+/* any mesh + partition vector (e.g. swe_partition_rcb); every rank passes the same inputs. 4 vertex rings. */
+SWE_API int swe_dist_plan_mesh(swe_dist_plan **out, int32_t rank, int32_t world, const swe_hostmesh *global,
+                               const int32_t *part_nt);
+SWE_API void swe_dist_plan_free(swe_dist_plan *plan);
+SWE_API const swe_hostmesh *swe_dist_plan_local_mesh(const swe_dist_plan *plan);   /* owned + halo cells   */
+SWE_API int64_t swe_dist_plan_owned_count(const swe_dist_plan *plan);
+SWE_API const uint8_t *swe_dist_plan_owned(const swe_dist_plan *plan);             /* per local cell       */
+SWE_API const int64_t *swe_dist_plan_global_cells(const swe_dist_plan *plan);      /* local -> global id   */
+SWE_API const uint8_t *swe_dist_plan_classes(const swe_dist_plan *plan);           /* ordering class 0..3  */
+SWE_API const uint8_t *swe_dist_plan_cfl_mask(const swe_dist_plan *plan);          /* per local edge       */
+SWE_API int32_t swe_dist_plan_npeers(const swe_dist_plan *plan);
+SWE_API int swe_dist_plan_peer(const swe_dist_plan *plan, int32_t k, int32_t *peer_rank, int64_t *nsend,
+                               const int64_t **send_local, int64_t *nrecv, const int64_t **recv_local);
+
+/* bootstrap: gather `bytes` bytes from every rank into recv (world * bytes, rank order). 0 = success. */
+typedef int (*swe_allgather_fn)(void *user, const void *send, void *recv, int64_t bytes);
+typedef struct swe_dist_config {
+    int32_t device;        /* CUDA device ordinal of this rank                                          */
+    int32_t reorder;       /* 1: Hilbert numbering inside every ordering class (default in the drivers)  */
+    int32_t overlap;       /* 1: the exchange overlaps the interior reconstruction / update (default)    */
+    int32_t reserved;
+    double cor, tau;       /* SpaceDisc ctor arguments                                                   */
+    double wait_timeout_s; /* peer waits give up after this long and raise SWE_ERR_CUDA (0: 60 s)        */
+    swe_allgather_fn allgather;
+    void *user;
+} swe_dist_config;
+
+/* one process per GPU: every rank calls this collectively with its own plan (takes ownership of it) */
+SWE_API int swe_dist_create(swe_dist **out, swe_dist_plan *plan, const swe_dist_config *cfg);
+/* one process, `world` GPUs: plans[r] / devices[r] per rank; out[r] receives the rank objects */
+SWE_API int swe_dist_group_create(swe_dist **out_world, swe_dist_plan **plans_world, const int32_t *devices_world,
+                                  int32_t world, const swe_dist_config *cfg);
+SWE_API void swe_dist_destroy(swe_dist *d);
+SWE_API const char *swe_dist_last_error(const swe_dist *d);
+SWE_API swe_ctx *swe_dist_ctx(swe_dist *d);                 /* the rank's device context (local numbering)   */
+SWE_API const swe_dist_plan *swe_dist_get_plan(const swe_dist *d);
+/* fill the halo cells from their owners (after swe_set_state / device-side initial conditions) */
+SWE_API int swe_dist_exchange(swe_dist *d);
+/* Solvers::Euler/SSPRK2/SSPRK3 on all ranks; asynchronous on each rank's stream. dt <= 0 in swe_dist_run:
+ * every step uses 0.15 * GLOBAL min_len_to_wavespeed of the previous step (device resident); first step dt0. */
+SWE_API int swe_dist_step(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt);
+SWE_API int swe_dist_run(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, int64_t nsteps, double dt,
+                         double dt0);
+/* group form: issues every step for all ranks of one process in turn */
+SWE_API int swe_dist_group_run(swe_dist **ranks, int32_t world, swe_scheme scheme, swe_flux flux, swe_wavespeed ws,
+                               int64_t nsteps, double dt, double dt0);
+/* waits for the rank's stream; SWE_ERR_NUMERIC on a non-finite state, SWE_ERR_CUDA if a peer wait timed out */
+SWE_API int swe_dist_synchronize(swe_dist *d);
+SWE_API int swe_dist_cfl_dt(swe_dist *d, double *dt);     /* 0.15 * global min (after a step)               */
+/* order-independent 64-bit hash of this rank's OWNED cell states keyed by global cell id: the sum over the
+ * ranks (mod 2^64) equals swe_state_hash of the undecomposed run iff every cell is bit-identical */
+SWE_API int swe_dist_state_hash(swe_dist *d, uint64_t *partial);
+SWE_API int swe_state_hash(swe_ctx *ctx, uint64_t *hash);
+/* owned cell states into a GLOBAL 3 x nt_global array (only this rank's owned columns are written) */
+SWE_API int swe_dist_get_owned_state(swe_dist *d, double *prim_3xnt_global);
+/* set the local state (owned + halo) from a GLOBAL 3 x nt_global array */
+SWE_API int swe_dist_set_state_global(swe_dist *d, const double *prim_3xnt_global);
+
+/* ------------------------------------------------------------------------------------ */
 /* Analytic test cases (examples/Tests.h) — bathymetry and initial conditions             */
 /* ------------------------------------------------------------------------------------ */
 typedef enum swe_case_kind {

@@ -71,6 +71,12 @@ def lib() -> C.CDLL:
         l.oracle_reconstruct.argtypes = [C.c_void_p, C.c_int, C.c_int64, _D, _D]
         l.oracle_muscl_at_point.argtypes = [C.c_void_p, C.c_int64, _D, _D, _D, _D]
         l.oracle_set_node_max_w.argtypes = [C.c_void_p, _D]
+        l.oracle_struct_mesh_sizes.argtypes = [C.c_int64, C.c_int64, _I64, _I64, _I64]
+        l.oracle_struct_mesh.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64, _D, _I64, _I64, _I64, _I64, _I64]
+        l.oracle_case_eval.argtypes = [C.c_int, _D, C.c_double, C.c_double, C.c_double, _D]
+        l.oracle_triang_average_poly.argtypes = [C.c_int, _D, _D, _D, _D, _D]
+        l.oracle_case_set_bathymetry.argtypes = [C.c_int, _D, C.c_int64, _D]
+        l.oracle_case_initial_state.argtypes = [C.c_int, _D, C.c_int64, _D, _I64, C.c_int, C.c_double, _D]
         _lib = l
     return _lib
 
@@ -242,3 +248,53 @@ class Oracle:
                 self._h = None
         except Exception:
             pass
+
+
+class OracleStructMesh:
+    """StructTriangMesh(ni, nj, h) generated by the oracle itself (closed form, conventions of SURVEY App. B):
+    same attributes as the product's mesh classes, no product code involved."""
+
+    def __init__(self, ni: int, nj: int, h: float, i0: int = 0, j0: int = 0):
+        l = lib()
+        nn, ne, nt = C.c_int64(), C.c_int64(), C.c_int64()
+        l.oracle_struct_mesh_sizes(ni, nj, C.byref(nn), C.byref(ne), C.byref(nt))
+        self.nn, self.ne, self.nt = nn.value, ne.value, nt.value
+        self.ni, self.nj, self.h = ni, nj, float(h)
+        self.geometry = np.empty((self.nn, 3))
+        self.edge_nodes = np.empty((self.ne, 2), dtype=np.int64)
+        self.edge_elements = np.empty((self.ne, 2), dtype=np.int64)
+        self.element_nodes = np.empty((self.nt, 3), dtype=np.int64)
+        self.element_edges = np.empty((self.nt, 3), dtype=np.int64)
+        self.element_neighbours = np.empty((self.nt, 3), dtype=np.int64)
+        l.oracle_struct_mesh(ni, nj, float(h), i0, j0, _d(self.geometry), _i(self.edge_nodes), _i(self.edge_elements),
+                             _i(self.element_nodes), _i(self.element_edges), _i(self.element_neighbours))
+
+
+class OracleCase:
+    """Analytic cases of examples/Tests.h restated for the oracle: bathymetry, exact solution, cell-average IC."""
+
+    KINDS = {"lake_at_rest": 0, "classic_thacker": 1, "gauss_wave": 2, "fully_wet": 3, "bowl_hump": 4}
+
+    def __init__(self, kind: str, mid_x: float, mid_y: float, length: float, cor=0.0, tau=0.0, delta=1.0, H0=0.5, p0=0.0,
+                 q0=0.0, level=0.0, amp=None):
+        self.kind = self.KINDS[kind]
+        if amp is None:
+            amp = 0.05 if kind == "fully_wet" else 0.0
+        self.par = np.array([mid_x, mid_y, length, cor, tau, delta, H0, p0, q0, level, amp], dtype=np.float64)
+
+    def eval(self, x, y, t=0.0):
+        out = np.empty(4)
+        lib().oracle_case_eval(self.kind, _d(self.par), x, y, t, _d(out))
+        return out
+
+    def set_bathymetry(self, mesh):
+        g = mesh.geometry
+        assert g.flags.c_contiguous
+        lib().oracle_case_set_bathymetry(self.kind, _d(self.par), mesh.nn, _d(g))
+
+    def initial_state(self, mesh, quad_n=4, t=0.0):
+        prim = np.empty((mesh.nt, 3))
+        g = np.ascontiguousarray(mesh.geometry, dtype=np.float64)
+        tp = np.ascontiguousarray(mesh.element_nodes, dtype=np.int64)
+        lib().oracle_case_initial_state(self.kind, _d(self.par), mesh.nt, _d(g), _i(tp), int(quad_n), float(t), _d(prim))
+        return prim

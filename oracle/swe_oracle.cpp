@@ -840,3 +840,220 @@ void oracle_muscl_at_point(void *p, int64_t i, const double *o3, const double *G
 void oracle_set_node_max_w(void *p, const double *in) { Oracle *o = static_cast<Oracle *>(p); std::copy(in, in + o->nn, o->maxwp.begin()); }
 
 }  // extern "C"
+
+// -------------------------------------------------------------------------------------------
+// Mesh generator + analytic cases + cell-average initial conditions, restated for the oracle so that
+// the CPU arm needs nothing from the product library (bench.py --impl reference) and so that the
+// product's host / device versions are checked against an independent statement.
+// -------------------------------------------------------------------------------------------
+namespace {
+
+// StructTriangMesh(ni, nj, h) (include/StructTriangMesh.h:4-15; body missing upstream): conventions of
+// SURVEY App. B recovered from notebooks/topology.dat — (ni+1)(nj+1) corner nodes row by row, then ni*nj
+// centre nodes; per square the triangles Bottom, Right, Top, Left, CCW, last node = centre; edges numbered
+// in order of first visit (triangles in order, k = 0,1,2, edge k joins nodes k and k+1); EdgePoints sorted;
+// EdgeTriangs = (later visitor, earlier visitor), boundary (owner, -1). Everything in closed form.
+struct StructIdx {
+    Idx ni, nj;
+    Idx row_base(Idx j) const { return j == 0 ? 0 : (7 * ni + 1) + (j - 1) * (6 * ni + 1); }
+    Idx sq_base(Idx j, Idx i) const { return row_base(j) + i * (j == 0 ? 7 : 6) + (i > 0 ? 1 : 0); }
+    Idx off(Idx j) const { return j == 0 ? 1 : 0; }
+    Idx e_b1(Idx j, Idx i) const { return sq_base(j, i) + off(j); }
+    Idx e_b2(Idx j, Idx i) const { return e_b1(j, i) + 1; }
+    Idx e_right(Idx j, Idx i) const { return e_b1(j, i) + 2; }
+    Idx e_r1(Idx j, Idx i) const { return e_b1(j, i) + 3; }
+    Idx e_top(Idx j, Idx i) const { return e_b1(j, i) + 4; }
+    Idx e_t1(Idx j, Idx i) const { return e_b1(j, i) + 5; }
+    Idx e_bot(Idx j, Idx i) const { return j == 0 ? sq_base(j, i) : e_top(j - 1, i); }
+    Idx e_left(Idx j, Idx i) const { return i == 0 ? e_b1(j, i) + 6 : e_right(j, i - 1); }
+};
+
+}  // namespace
+
+extern "C" {
+
+void oracle_struct_mesh_sizes(int64_t ni, int64_t nj, int64_t *nn, int64_t *ne, int64_t *nt) {
+    *nn = (ni + 1) * (nj + 1) + ni * nj; *ne = 6 * ni * nj + ni + nj; *nt = 4 * ni * nj;
+}
+void oracle_struct_mesh(int64_t ni, int64_t nj, double h, int64_t i0, int64_t j0, double *geom, int64_t *ep, int64_t *et,
+                        int64_t *tp, int64_t *te, int64_t *tt) {
+    const Idx nv = (ni + 1) * (nj + 1);
+    const StructIdx S{ni, nj};
+#pragma omp parallel for schedule(static)
+    for (Idx j = 0; j <= nj; ++j)
+        for (Idx i = 0; i <= ni; ++i) {
+            double *g = &geom[3 * (j * (ni + 1) + i)];
+            g[0] = double(i0 + i) * h; g[1] = double(j0 + j) * h; g[2] = 0.;
+        }
+#pragma omp parallel for schedule(static)
+    for (Idx j = 0; j < nj; ++j)
+        for (Idx i = 0; i < ni; ++i) {
+            const Idx s = j * ni + i;
+            double *g = &geom[3 * (nv + s)];
+            g[0] = (double(i0 + i) + 0.5) * h; g[1] = (double(j0 + j) + 0.5) * h; g[2] = 0.;
+            const Idx v00 = j * (ni + 1) + i, v10 = v00 + 1, v01 = v00 + ni + 1, v11 = v01 + 1, c = nv + s;
+            const Idx B = 4 * s, R = B + 1, T = B + 2, L = B + 3;
+            const Idx P[4][3] = {{v00, v10, c}, {v10, v11, c}, {v11, v01, c}, {v01, v00, c}};
+            const Idx bot = S.e_bot(j, i), b1 = S.e_b1(j, i), b2 = S.e_b2(j, i), rgt = S.e_right(j, i), r1 = S.e_r1(j, i),
+                      top = S.e_top(j, i), t1 = S.e_t1(j, i), lft = S.e_left(j, i);
+            const Idx E[4][3] = {{bot, b1, b2}, {rgt, r1, b1}, {top, t1, r1}, {lft, b2, t1}};
+            const Idx below = j > 0 ? 4 * (s - ni) + 2 : -1, east = i < ni - 1 ? 4 * (s + 1) + 3 : -1,
+                      above = j < nj - 1 ? 4 * (s + ni) : -1, west = i > 0 ? 4 * (s - 1) + 1 : -1;
+            const Idx N[4][3] = {{below, R, L}, {east, T, B}, {above, L, R}, {west, B, T}};
+            for (int q = 0; q < 4; ++q)
+                for (int k = 0; k < 3; ++k) { tp[3 * (B + q) + k] = P[q][k]; te[3 * (B + q) + k] = E[q][k]; tt[3 * (B + q) + k] = N[q][k]; }
+            auto edge = [&](Idx e, Idx a, Idx b, Idx later, Idx earlier) {
+                ep[2 * e] = std::min(a, b); ep[2 * e + 1] = std::max(a, b);
+                et[2 * e] = later; et[2 * e + 1] = earlier;
+            };
+            // every edge is written by exactly one square: the one that visits it first
+            if (j == 0) edge(bot, v00, v10, B, -1);
+            edge(b1, v10, c, R, B);
+            edge(b2, c, v00, L, B);
+            edge(rgt, v10, v11, i < ni - 1 ? east : R, i < ni - 1 ? R : -1);
+            edge(r1, v11, c, T, R);
+            edge(top, v11, v01, j < nj - 1 ? above : T, j < nj - 1 ? T : -1);
+            edge(t1, v01, c, L, T);
+            if (i == 0) edge(lft, v01, v00, L, -1);
+        }
+}
+
+// examples/Tests.h: kind 0 LakeAtRestTest (:32-43), 1 ClassicThackerTest (:46-57,135-162,237-280), 2 the Gaussian
+// hump of testGaussWave (examples/Main.cpp:183-186, flat bed), 3 the synthetic fully-wet workload of SURVEY §8d,
+// 4 BowlTest bed + still lake + hump. par = (mid_x, mid_y, length, cor, tau, delta, H0, p0, q0, level, amp).
+// out = (b, h, u, v) at (x, y, t).
+void oracle_case_eval(int kind, const double *par, double x, double y, double t, double *out) {
+    const double mx = par[0], my = par[1], len = par[2], cor = par[3], delta = par[5], H0 = par[6], p0 = par[7], q0 = par[8],
+                 level = par[9], amp = par[10];
+    double b = 0., h = 0., u = 0., v = 0.;
+    if (kind == 0) {
+        b = (1. < x) && (x < 3.) && (1. < y) && (y < 3.) ? -0.2 : -1.;
+        h = std::max(0., -b);
+    } else if (kind == 1) {
+        b = delta * ((x - mx) * (x - mx) + (y - my) * (y - my) - 1.0);
+        const double w = std::sqrt(cor * cor + 8. * delta);
+        const double qz = (q0 - 0.5 * cor) * (q0 - 0.5 * cor);
+        const double rz = qz + 2. * H0 * H0 + p0 * p0 - 0.25 * w * w;
+        const double a = std::sqrt(rz * rz + w * w * p0 * p0) / (rz + 0.5 * w * w);
+        const double bb = std::atan(w * p0 / rz);
+        const double p = 0.5 * w * a * std::sin(w * t + bb) / (1. - a * std::cos(w * t + bb));
+        const double q = (q0 - 0.5 * cor) * (1. - a * std::cos(bb)) / (1. - a * std::cos(w * t + bb)) + 0.5 * cor;
+        u = p * (x - mx) + q * (y - my);
+        v = q * (mx - x) + p * (y - my);
+        const double Hc = H0 * (1. - a * std::cos(bb)) / (1. - a * std::cos(w * t + bb));
+        const double az0 = (1. - a * std::cos(bb)) * (1. - a * std::cos(bb));
+        const double azt = (1. - a * std::cos(w * t + bb)) * (1. - a * std::cos(w * t + bb));
+        const double Hxx = (0.25 * w * w * (a * a - 1.) + qz * az0) / azt, Hyy = Hxx, Hxy = 0.;
+        const double res = Hc + 0.5 * Hxx * (x - mx) * (x - mx) + Hxy * (x - mx) * (y - my) + 0.5 * Hyy * (y - my) * (y - my);
+        h = std::max(0., res);
+    } else if (kind == 2) {
+        h = 1. + std::exp(-5. * ((x - mx) * (x - mx) + (y - my) * (y - my)));
+    } else if (kind == 3) {
+        const double two_pi = 6.283185307179586476925286766559;
+        b = 0.1 * std::sin(two_pi * x / len) * std::sin(two_pi * y / len) - 1.;
+        h = amp * std::exp(-5. * ((x - mx) * (x - mx) + (y - my) * (y - my))) - b;
+    } else {
+        b = delta * ((x - mx) * (x - mx) + (y - my) * (y - my) - 1.0);
+        h = std::max(0., level + amp * std::exp(-5. * ((x - mx) * (x - mx) + (y - my) * (y - my))) - b);
+    }
+    out[0] = b; out[1] = h; out[2] = u; out[3] = v;
+}
+
+}  // extern "C"
+
+namespace {
+// TriangAverage<3,n> (include/PointOperations.h:20-44), n at run time: n^2 congruent sub-triangles, the integrand at
+// every sub-centroid, in upstream's loop and accumulation order (sum += h*f; result h*sum).
+template <class F>
+void TriangAverage3(int n, const double *p0, const double *p1, const double *p2, const F &f, double out[3]) {
+    const double h = 1. / n;
+    double di[3], dj[3], dt[3], pi[3], sum[3] = {0., 0., 0.};
+    for (int c = 0; c < 3; ++c) {
+        di[c] = h * (p1[c] - p0[c]); dj[c] = h * (p2[c] - p0[c]);
+        dt[c] = 1. / 3. * (di[c] + dj[c]); pi[c] = p0[c];
+    }
+    double v[3], q[3];
+    for (int i = 0; i < n; i++) {
+        double pt[3] = {pi[0] + dt[0], pi[1] + dt[1], pi[2] + dt[2]};
+        for (int j = 0; j < n - i - 1; j++) {
+            f(pt, v);
+            for (int c = 0; c < 3; ++c) sum[c] += h * v[c];
+            for (int c = 0; c < 3; ++c) q[c] = pt[c] + dt[c];
+            f(q, v);
+            for (int c = 0; c < 3; ++c) sum[c] += h * v[c];
+            for (int c = 0; c < 3; ++c) pt[c] += dj[c];
+        }
+        f(pt, v);
+        for (int c = 0; c < 3; ++c) sum[c] += h * v[c];
+        for (int c = 0; c < 3; ++c) pi[c] += di[c];
+    }
+    for (int c = 0; c < 3; ++c) out[c] = h * sum[c];
+}
+}  // namespace
+
+extern "C" {
+
+// polynomial test integrand (coefficients c[0..5]) for the bit comparison with upstream's TriangAverage
+void oracle_triang_average_poly(int n, const double *p0, const double *p1, const double *p2, const double *c, double *out3) {
+    TriangAverage3(n, p0, p1, p2, [c](const double *q, double *v) {
+        v[0] = c[0] + c[1] * q[0] + c[2] * q[1] * q[1]; v[1] = c[3] * q[0] * q[1]; v[2] = c[4] + c[5] * q[2];
+    }, out3);
+}
+
+// nodal bathymetry geometry row 2 <- b(x, y) (examples/Main.cpp:204-207, 319-322)
+void oracle_case_set_bathymetry(int kind, const double *par, int64_t nn, double *geom) {
+#pragma omp parallel for schedule(static)
+    for (Idx n = 0; n < nn; ++n) {
+        double o[4];
+        oracle_case_eval(kind, par, geom[3 * n], geom[3 * n + 1], 0., o);
+        geom[3 * n + 2] = o[0];
+    }
+}
+
+// cell initial state like examples/Main.cpp:211-223: (h, u, v) averaged by TriangAverage<3, quad_n> at time t,
+// then w = h_avg + b_i, through PrimAssigner (src/Assigners.cpp:8-20). LakeAtRest: the average of max(0, bed)
+// over the cell (examples/Main.cpp:333-336); the Gaussian wave samples w at the centroid (:183-186).
+void oracle_case_initial_state(int kind, const double *par, int64_t nt, const double *geom, const int64_t *tp, int quad_n,
+                               double t, double *prim) {
+    const double third = 1. / 3.;
+#pragma omp parallel for schedule(static)
+    for (Idx i = 0; i < nt; ++i) {
+        const double *p0 = &geom[3 * tp[3 * i]], *p1 = &geom[3 * tp[3 * i + 1]], *p2 = &geom[3 * tp[3 * i + 2]];
+        const double cx = p0[0] * third + p1[0] * third + p2[0] * third;
+        const double cy = p0[1] * third + p1[1] * third + p2[1] * third;
+        const double bi = p0[2] * third + p1[2] * third + p2[2] * third;
+        double x[3] = {0., 0., 0.};
+        if (kind == 2) {
+            double o[4];
+            oracle_case_eval(kind, par, cx, cy, t, o);
+            x[0] = o[1];
+        } else if (kind == 0) {
+            if (!(p0[2] <= 0. && p1[2] <= 0. && p2[2] <= 0.)) {
+                const double det = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (p1[1] - p0[1]);
+                TriangAverage3(quad_n, p0, p1, p2, [&](const double *q, double *v) {
+                    const double l1 = ((q[0] - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (q[1] - p0[1])) / det;
+                    const double l2 = ((p1[0] - p0[0]) * (q[1] - p0[1]) - (q[0] - p0[0]) * (p1[1] - p0[1])) / det;
+                    v[0] = std::max(0., p0[2] + l1 * (p1[2] - p0[2]) + l2 * (p2[2] - p0[2])); v[1] = 0.; v[2] = 0.;
+                }, x);
+            }
+            x[1] = 0.; x[2] = 0.;
+        } else {
+            TriangAverage3(quad_n, p0, p1, p2, [&](const double *q, double *v) {
+                double o[4];
+                oracle_case_eval(kind, par, q[0], q[1], t, o);
+                v[0] = o[1]; v[1] = o[2]; v[2] = o[3];
+            }, x);
+            x[0] += bi;
+        }
+        const double h = x[0] - bi;
+        double *o = &prim[3 * i];
+        if (!IsWet(h)) { o[0] = bi; o[1] = 0.; o[2] = 0.; continue; }
+        o[0] = x[0]; o[1] = x[1]; o[2] = x[2];
+        if (h < 1e-3) {
+            const double f = std::sqrt(2) * h / std::sqrt(h * h + 1e-6);
+            o[1] *= f; o[2] *= f;
+        }
+    }
+}
+
+}  // extern "C"

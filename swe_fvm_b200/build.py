@@ -8,8 +8,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libswe_b200.so")
-SOURCES = ["swe_b200.cu", "hostmesh.cpp"]
-HEADERS = ["swe_kernels.cuh", "swe_device.cuh", "swe_cases.cuh", "hostmesh.hpp", os.path.join("..", "..", "include", "swe_b200.h")]
+SOURCES = ["swe_b200.cu", "hostmesh.cpp", "distplan.cpp"]
+HEADERS = ["swe_kernels.cuh", "swe_device.cuh", "swe_cases.cuh", "swe_dist.cuh", "hostmesh.hpp", "distplan.hpp", os.path.join("..", "..", "include", "swe_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

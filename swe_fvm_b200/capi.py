@@ -47,6 +47,17 @@ class MeshStruct(C.Structure):  # struct swe_mesh
     ]
 
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)  # swe_allgather_fn
+
+
+class DistConfig(C.Structure):  # struct swe_dist_config
+    _fields_ = [
+        ("device", C.c_int32), ("reorder", C.c_int32), ("overlap", C.c_int32), ("reserved", C.c_int32),
+        ("cor", C.c_double), ("tau", C.c_double), ("wait_timeout_s", C.c_double),
+        ("allgather", ALLGATHER_FN), ("user", C.c_void_p),
+    ]
+
+
 class CaseStruct(C.Structure):  # struct swe_case
     _fields_ = [
         ("kind", C.c_int32),
@@ -114,6 +125,33 @@ SYMBOLS = {
     "swe_halo_p2p_error": (C.c_int, [_P]),
     "swe_set_min_len_to_wavespeed": (C.c_int, [_P, C.c_double]),
     "swe_min_len_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
+    "swe_dist_plan_struct": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_double]),
+    "swe_dist_plan_mesh": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, _P, _I32]),
+    "swe_dist_plan_free": (None, [_P]),
+    "swe_dist_plan_local_mesh": (_P, [_P]),
+    "swe_dist_plan_owned_count": (C.c_int64, [_P]),
+    "swe_dist_plan_owned": (_U8, [_P]),
+    "swe_dist_plan_global_cells": (_I64, [_P]),
+    "swe_dist_plan_classes": (_U8, [_P]),
+    "swe_dist_plan_cfl_mask": (_U8, [_P]),
+    "swe_dist_plan_npeers": (C.c_int32, [_P]),
+    "swe_dist_plan_peer": (C.c_int, [_P, C.c_int32, _I32, _I64, C.POINTER(_I64), _I64, C.POINTER(_I64)]),
+    "swe_dist_create": (C.c_int, [C.POINTER(_P), _P, C.POINTER(DistConfig)]),
+    "swe_dist_group_create": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _I32, C.c_int32, C.POINTER(DistConfig)]),
+    "swe_dist_destroy": (None, [_P]),
+    "swe_dist_last_error": (C.c_char_p, [_P]),
+    "swe_dist_ctx": (_P, [_P]),
+    "swe_dist_get_plan": (_P, [_P]),
+    "swe_dist_exchange": (C.c_int, [_P]),
+    "swe_dist_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "swe_dist_run": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double]),
+    "swe_dist_group_run": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double]),
+    "swe_dist_synchronize": (C.c_int, [_P]),
+    "swe_dist_cfl_dt": (C.c_int, [_P, _D]),
+    "swe_dist_state_hash": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "swe_state_hash": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "swe_dist_get_owned_state": (C.c_int, [_P, _D]),
+    "swe_dist_set_state_global": (C.c_int, [_P, _D]),
     "swe_hostmesh_struct": (C.c_int, [C.POINTER(_P), C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64]),
     "swe_hostmesh_gmsh": (C.c_int, [C.POINTER(_P), C.c_char_p]),
     "swe_hostmesh_from_triangles": (C.c_int, [C.POINTER(_P), C.c_int64, _D, C.c_int64, _I64, C.c_int64, _I64]),

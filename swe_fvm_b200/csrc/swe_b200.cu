@@ -33,7 +33,7 @@ struct swe_ctx {
     bool reordered = false;
     bool taps = false;
     int opt_recon = 0, opt_pw2 = 0, opt_roe_fix = 0, opt_cfl_abs = 0;  // swe_set_option (semantic decisions S2/S3/S5/S6)
-    int opt_tiled = SWE_K1_TILED;                                      // K1 form: 1 = shared-memory staged tiles (TMA), 0 = gathers
+    int opt_tiled = 0;  // K1 form: 0 = register-prefetched gathers (default, faster: profiles/r2_k1_tiled_vs_gather.md), 1 = TMA-staged tiles
     unsigned long long *dbg = nullptr;                                 // branch-hit counters (taps)
     int class_first[6] = {0, 0, 0, 0, 0, 0};  // device cell range of every ordering class
     // device mesh
@@ -230,6 +230,34 @@ static void launch_flux_ws(swe_ctx *c, const DevMesh &m, const DevFields &s, int
     }
 }
 
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY): the first launch of a kernel may have to wait for every
+// running kernel to finish. A rank that spins in k_halo_wait_unpack / k_min_pull for a peer of the SAME process
+// would then dead-lock the host thread that is about to issue that peer's first k_min_push. So every kernel
+// of the time step is loaded once, up front, when the first context is created.
+static void preload_kernels() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    cudaFuncAttributes a;
+#define SWE_LOAD(...) cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__))
+#define SWE_LOAD_K1(T) SWE_LOAD(k_reconstruct<T, 0>); SWE_LOAD(k_reconstruct<T, 1>); SWE_LOAD(k_reconstruct<T, 2>); \
+    SWE_LOAD(k_reconstruct_tiled<T, 0>); SWE_LOAD(k_reconstruct_tiled<T, 1>); SWE_LOAD(k_reconstruct_tiled<T, 2>); \
+    SWE_LOAD(k_reconstruct_slow<T>); SWE_LOAD(k_partwet2<T>)
+    SWE_LOAD_K1(false); SWE_LOAD_K1(true);
+#define SWE_LOAD_K2(F, O) SWE_LOAD(k_flux<F, WS_RUSANOV, O>); SWE_LOAD(k_flux<F, WS_DAVIS, O>); SWE_LOAD(k_flux<F, WS_EINFELDT, O>)
+    SWE_LOAD_K2(FLUX_HLL, false); SWE_LOAD_K2(FLUX_HLL, true); SWE_LOAD_K2(FLUX_HLLC, false); SWE_LOAD_K2(FLUX_HLLC, true);
+    SWE_LOAD(k_drain);
+    SWE_LOAD(k_update<true, true>); SWE_LOAD(k_update<true, false>); SWE_LOAD(k_update<false, true>); SWE_LOAD(k_update<false, false>);
+    SWE_LOAD(k_post_step); SWE_LOAD(k_set_scalar);
+    SWE_LOAD(k_halo_pack); SWE_LOAD(k_halo_unpack); SWE_LOAD(k_halo_signal); SWE_LOAD(k_halo_wait);
+    SWE_LOAD(k_halo_pack_signal); SWE_LOAD(k_halo_wait_unpack); SWE_LOAD(k_min_push); SWE_LOAD(k_min_pull);
+    SWE_LOAD(k_state_hash); SWE_LOAD(k_state_in); SWE_LOAD(k_state_out); SWE_LOAD(k_diag_partial); SWE_LOAD(k_diag_final);
+#undef SWE_LOAD_K2
+#undef SWE_LOAD_K1
+#undef SWE_LOAD
+    cudaGetLastError();
+}
+
 extern "C" {
 
 SWE_API const char *swe_version(void) { return "swe_b200 0.1 (sm_100a, fp64, -fmad=false)"; }
@@ -287,6 +315,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail(SWE_ERR_CUDA, cudaGetErrorString(ce));
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+    preload_kernels();
 
     swe_ctx *c = new (std::nothrow) swe_ctx();
     if (!c) return fail(SWE_ERR_NOMEM, "out of host memory");
@@ -688,7 +717,9 @@ SWE_API int swe_save_state(swe_ctx *c) {
     return SWE_OK;
 }
 
-static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double dt_coef) {
+// K3 over all cells, then the choice of the output buffer of this stage (first stage after
+// swe_save_state: the other buffer, so that U0 stays intact without a copy kernel)
+static int stage_drain(swe_ctx *c, double ***outb_out) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
@@ -698,15 +729,23 @@ static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double
     kt_end(c, kt);
     if ((rc = launch_check(c, "k_drain"))) return rc;
     double **outb = c->cur;
-    if (c->saved_pending && c->sav == c->cur) {  // first stage after save: keep U0 intact
+    if (c->saved_pending && c->sav == c->cur) {
         outb = (c->cur == c->bufA) ? c->bufB : c->bufA;
         c->saved_pending = false;
     }
-    const int g = nblk(c->nt, kBlock);
-    kt = kt_begin(c, KT_UPDATE);
+    *outb_out = outb;
+    return SWE_OK;
+}
+// K4 on the device cell range [first, last)
+static int stage_update_range(swe_ctx *c, double **outb, double a0, double a1, double dt_host, double dt_coef, int first, int last) {
+    if (last <= first) return SWE_OK;
+    const DevMesh m = dev_mesh(c);
+    const DevFields s = dev_fields(c);
+    const int g = nblk(last - first, kBlock);
+    const int kt = kt_begin(c, KT_UPDATE);
     const bool cor_on = c->cor != 0.;
 #define SWE_UPD(PLAIN, COR, W0, U0, V0) \
-    k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor)
+    k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last)
     if (a0 == 0.) {
         if (cor_on) SWE_UPD(true, true, nullptr, nullptr, nullptr); else SWE_UPD(true, false, nullptr, nullptr, nullptr);
     } else {
@@ -714,7 +753,13 @@ static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double
     }
 #undef SWE_UPD
     kt_end(c, kt);
-    if ((rc = launch_check(c, "k_update"))) return rc;
+    return launch_check(c, "k_update");
+}
+static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double dt_coef) {
+    double **outb = nullptr;
+    int rc;
+    if ((rc = stage_drain(c, &outb))) return rc;
+    if ((rc = stage_update_range(c, outb, a0, a1, dt_host, dt_coef, 0, c->nt))) return rc;
     c->cur = outb;
     return SWE_OK;
 }
@@ -1099,3 +1144,5 @@ SWE_API int swe_halo_p2p_error(swe_ctx *c) {
 }
 
 }  // extern "C"
+
+#include "swe_dist.cuh"

@@ -740,10 +740,10 @@ template <bool PLAIN, bool COR>
 __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m, DevFields s, const double *__restrict__ w0,
                                                    const double *__restrict__ u0, const double *__restrict__ v0,
                                                    double *wout, double *uout, double *vout, double a0, double a1,
-                                                   double dt_host, double dt_coef, double cor) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   double dt_host, double dt_coef, double cor, int first, int last) {
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;  // cell range [first, last) in device numbering
     const int nt = m.nt;
-    if (i >= nt) return;
+    if (i >= last) return;
     // All loads are issued before any arithmetic (ids -> gathers: two dependent round trips, every
     // gather of the cell in flight at once). Written out explicitly because the compiler's own
     // schedule flipped between a batched (2.2 ms) and an interleaved (2.6 ms at 64M cells) form
@@ -974,6 +974,105 @@ __global__ void k_halo_wait(volatile int *flags, int npeers, int seq, long long 
         __nanosleep(200);
     }
     __threadfence_system();
+}
+
+// Fused send side of the peer-memory transport: pack this rank's boundary states straight into the
+// neighbour GPU's receive buffer (NVLink stores) and, from the last block to finish, publish the
+// exchange number in the neighbour's flag slot. One launch per peer, right after the boundary cells were
+// updated, so the stores fly while the interior is still being updated.
+__global__ void k_halo_pack_signal(int n, const int *cells, const double *w, const double *u, const double *v, double *peer_buf,
+                                   volatile int *peer_flag, int seq, int *ticket) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const int c = cells[k];
+        peer_buf[3 * (size_t)k] = w[c]; peer_buf[3 * (size_t)k + 1] = u[c]; peer_buf[3 * (size_t)k + 2] = v[c];
+    }
+    __threadfence_system();  // this thread's remote stores are visible system-wide before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        if (t == (int)gridDim.x - 1) {
+            *ticket = 0;
+            __threadfence_system();
+            *peer_flag = seq;
+            __threadfence_system();
+        }
+    }
+}
+// Fused receive side: every block waits until all peers have published `seq` (time-out: err[0] = 1 instead
+// of hanging), then the grid unpacks the receive buffer into the halo cells. Buffer reads bypass L1 (the
+// data was written by another GPU).
+__global__ void k_halo_wait_unpack(volatile int *flags, int npeers, int seq, long long timeout_cycles, int *err, int n,
+                                   const int *cells, const double *buf, double *w, double *u, double *v) {
+    if ((int)threadIdx.x < npeers) {
+        const long long t0 = clock64();
+        while (flags[threadIdx.x] < seq) {
+            if (clock64() - t0 > timeout_cycles) { err[0] = 1; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int c = cells[k];
+        w[c] = __ldcg(buf + 3 * (size_t)k); u[c] = __ldcg(buf + 3 * (size_t)k + 1); v[c] = __ldcg(buf + 3 * (size_t)k + 2);
+    }
+}
+// Global CFL minimum over peer memory (one double per rank, no NCCL on the path): push stores this rank's
+// min_len_to_wavespeed into slot [seq & 1][rank] of EVERY rank's table and then raises that rank's flag;
+// pull waits for all world flags and takes the minimum (exact, order independent => the same dt on every
+// GPU count). Double buffering by the parity of seq suffices: a rank cannot push step n+2 before every rank
+// has pulled step n (each pull needs every rank's push of the same step).
+constexpr int kMaxRanks = 16;
+struct MinPeers { double *buf[kMaxRanks]; int *flag[kMaxRanks]; };
+__global__ void k_min_push(const double *scal, MinPeers t, int world, int rank, int seq) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    t.buf[p][(seq & 1) * kMaxRanks + rank] = scal[0];
+    __threadfence_system();
+    *(volatile int *)(t.flag[p] + rank) = seq;
+    __threadfence_system();
+}
+__global__ void k_min_pull(double *scal, const double *buf, volatile int *flag, int world, int seq, long long timeout_cycles, int *err) {
+    const int p = threadIdx.x;
+    if (p < world) {
+        const long long t0 = clock64();
+        while (flag[p] < seq) {
+            if (clock64() - t0 > timeout_cycles) { err[0] = 1; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mn = __ldcg(buf + (seq & 1) * kMaxRanks);
+        for (int q = 1; q < world; ++q) { const double x = __ldcg(buf + (seq & 1) * kMaxRanks + q); mn = (x < mn) ? x : mn; }
+        scal[0] = mn;
+    }
+}
+
+// Order-independent 64-bit hash of the cell states: sum over the selected cells of mix(global id, component,
+// bit pattern). Equal on any partition of the same global mesh iff every owned cell state is bit-identical.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_state_hash(int nt, const int *old, const long long *gid, const unsigned char *mask, const double *w,
+                             const double *u, const double *v, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+        const int o = old ? old[i] : i;  // caller (local) id
+        if (mask && !mask[o]) continue;
+        const unsigned long long g = gid ? (unsigned long long)gid[o] : (unsigned long long)o;
+        acc += mix64(mix64(3ull * g) ^ (unsigned long long)__double_as_longlong(w[i]));
+        acc += mix64(mix64(3ull * g + 1ull) ^ (unsigned long long)__double_as_longlong(u[i]));
+        acc += mix64(mix64(3ull * g + 2ull) ^ (unsigned long long)__double_as_longlong(v[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -14,8 +14,9 @@ class TriangMesh:
     """Owning triangular mesh: node geometry (x, y, b) and the five Topology incidence arrays
     (include/TriangMesh.h:27-33) as numpy views into C++-owned memory."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, owner=True):
         self._h = handle
+        self._owner = owner  # False: a view of a mesh owned by someone else (e.g. a decomposition plan)
         self._view = capi.MeshStruct()
         capi.check(capi.lib().swe_hostmesh_view(self._h, C.byref(self._view)))
         v = self._view
@@ -96,9 +97,9 @@ class TriangMesh:
 
     def __del__(self):
         try:
-            if self._h:
+            if self._h and self._owner:
                 capi.lib().swe_hostmesh_free(self._h)
-                self._h = None
+            self._h = None
         except Exception:
             pass
 

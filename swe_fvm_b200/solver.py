@@ -44,6 +44,24 @@ class SpaceDisc:
         if v0 is not None:
             self.SetVolField(v0)
 
+    @classmethod
+    def from_ctx(cls, ctx_ptr, mesh, flux="hllc", wavespeed="einfeldt", cor=0.0, tau=0.0) -> "SpaceDisc":
+        """View of a device context owned by someone else (a swe_dist rank); never destroys it."""
+        self = cls.__new__(cls)
+        self.flux = capi.FLUXES[flux.lower()] if isinstance(flux, str) else int(flux)
+        self.wavespeed = capi.WAVESPEEDS[wavespeed.lower()] if isinstance(wavespeed, str) else int(wavespeed)
+        self.mesh = mesh
+        self.nt, self.ne, self.nn = mesh.nt, mesh.ne, mesh.nn
+        self.cor, self.tau = float(cor), float(tau)
+        self._ctx = C.c_void_p(ctx_ptr)
+        self._borrowed = True
+        return self
+
+    def state_hash(self) -> int:
+        v = C.c_uint64()
+        self._call("swe_state_hash", C.byref(v))
+        return int(v.value)
+
     # -- plumbing --
     def _call(self, name, *args):
         capi.check(getattr(capi.lib(), name)(self._ctx, *args), self._ctx)
@@ -180,7 +198,8 @@ class SpaceDisc:
 
     def close(self):
         if getattr(self, "_ctx", None):
-            capi.lib().swe_destroy(self._ctx)
+            if not getattr(self, "_borrowed", False):
+                capi.lib().swe_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):

@@ -1,5 +1,5 @@
 """Worker of tests/test_dist_cpu.py: one rank of a world_size-N gloo job. Runs the product's
-decomposition + DistributedSolver with the CPU oracle as the local solver and writes the owned
+C++ decomposition plan + the test-side stage loop with the CPU oracle as the local solver and writes the owned
 cells' final state (with global ids) to <out>.<rank>.npz."""
 import os
 import sys
@@ -23,29 +23,25 @@ def main():
 
     if mode == "strips":
         n = 24
-        dec = swd.decompose_strips(n, n, 4.0 / n, rank, world)
+        plan = swd.Plan.struct(rank, world, n, n, 4.0 / n)
         case = Case("classic_thacker", 2.0, 2.0, 4.0)
-        cells_per_row = 4 * n
-        lo = (swd.strip_rows(n, world)[rank][0] - swd.HALO_ROWS)
-        lo = max(lo, 0)
-        gids = np.arange(dec.mesh.nt) + lo * cells_per_row
     else:
         g = TriangMesh.from_gmsh(os.path.join(ROOT, "tests", "golden", "bowl.msh"))
         case = Case("bowl_hump", 4.0, 4.0, 8.0, level=3.0, amp=0.5)
         case.set_bathymetry(g)
-        part = g.partition_rcb(world)
-        dec = swd.decompose_general(g, part, rank, world)
-        gids = dec.global_cells
-    case.set_bathymetry(dec.mesh)
-    v0 = case.initial_state(dec.mesh, quad_n=4)
-    o = Oracle(dec.mesh)
+        plan = swd.Plan.from_mesh(rank, world, g, g.partition_rcb(world))
+    gids = plan.global_cells
+    case.set_bathymetry(plan.mesh)
+    v0 = case.initial_state(plan.mesh, quad_n=4)
+    o = Oracle(plan.mesh)
     o.set_state(v0)
     local = OracleLocal(o)
-    solver = swd.DistributedSolver(dec, local)
+    from dist_helpers import EmulatedSolver
+    solver = EmulatedSolver(plan, local)
     solver.run(scheme, nsteps, None if adaptive else 2e-3, dt0=1e-3)
     st = o.get_state()
-    np.savez(f"{out}.{rank}.npz", gids=gids[dec.owned], state=st[dec.owned], dt=local.dt,
-             minlen=float(local._ml[0]), exchanges=solver.exchanges, nsend=solver.halo.nsend, nrecv=solver.halo.nrecv)
+    np.savez(f"{out}.{rank}.npz", gids=gids[plan.owned], state=st[plan.owned], dt=local.dt,
+             minlen=float(local._ml[0]), exchanges=solver.exchanges, nsend=solver.nsend, nrecv=solver.nrecv)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,5 +1,5 @@
-"""Worker of tests/test_gpu_dist.py::test_nccl_*: one rank (= one GPU) of an NCCL job running the
-product's DistributedSolver on the device; writes the owned cells' final state per rank."""
+"""Worker of tests/test_gpu_dist.py::test_two_gpus_*: one rank (= one GPU, one process) of a torchrun job
+running swe_dist (peer memory over CUDA IPC); torch.distributed is only the bootstrap all-gather."""
 import os
 import sys
 
@@ -19,36 +19,27 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     from swe_fvm_b200 import Case, TriangMesh
     from swe_fvm_b200 import dist as swd
-    from swe_fvm_b200.solver import SpaceDisc
 
     if mode == "strips":
         n = 64
-        dec = swd.decompose_strips(n, n, 4.0 / n, rank, world)
+        plan = swd.Plan.struct(rank, world, n, n, 4.0 / n)
         case = Case("classic_thacker", 2.0, 2.0, 4.0)
-        lo = max(swd.strip_rows(n, world)[rank][0] - swd.HALO_ROWS, 0)
-        gids = np.arange(dec.mesh.nt) + lo * 4 * n
     else:
         g = TriangMesh.from_gmsh(os.path.join(ROOT, "tests", "golden", "bowl.msh"))
         case = Case("bowl_hump", 4.0, 4.0, 8.0, level=3.0, amp=0.5)
         case.set_bathymetry(g)
-        part = g.partition_rcb(world)
-        dec = swd.decompose_general(g, part, rank, world)
-        gids = dec.global_cells
-    case.set_bathymetry(dec.mesh)
-    v0 = case.initial_state(dec.mesh, quad_n=4)
-    sd = SpaceDisc("hllc", "einfeldt", dec.mesh, v0, device=local_rank, reorder=(mode != "strips"),
-                   cell_class=dec.cell_classes())
-    sd.set_stream(torch.cuda.current_stream().cuda_stream)
-    local = swd.GpuLocal(sd, has_classes=True)
-    transport = os.environ.get("SWE_HALO", "nccl")
-    solver = swd.DistributedSolver(dec, local, transport=transport)
-    assert solver.halo.transport == transport
-    solver.run(scheme, nsteps, None if adaptive else 2e-3, dt0=1e-3)
-    sd.synchronize()
-    assert not local.p2p_error()
-    st = sd.GetVolField()
-    np.savez(f"{out}.{rank}.npz", gids=gids[dec.owned], state=st[dec.owned], minlen=float(local.min_len_tensor().item()))
+        plan = swd.Plan.from_mesh(rank, world, g, g.partition_rcb(world))
+    case.set_bathymetry(plan.mesh)
+    v0 = case.initial_state(plan.mesh, quad_n=4)
+    ds = swd.DistSolver(plan, device=local_rank, reorder=(mode != "strips"), wait_timeout_s=30.0)
+    ds.sd.SetVolField(v0)
+    ds.exchange()
+    ds.run(scheme, nsteps, dt=0.0 if adaptive else 2e-3, dt0=1e-3)
+    ds.synchronize()
+    gids, st = ds.owned_state()
+    np.savez(f"{out}.{rank}.npz", gids=gids, state=st, hash=np.uint64(ds.state_hash()), dt=ds.cfl_dt())
     dist.barrier()
+    ds.close()
     dist.destroy_process_group()
 
 

@@ -56,3 +56,62 @@ class OracleLocal:
     def advance_dt(self, dt):
         if dt is None:
             self.dt = 0.15 * float(self._ml[0])
+
+
+class EmulatedSolver:
+    """Test-side stage loop of the multi-rank step over torch.distributed (gloo) with any local solver
+    (here the CPU oracle): the host logic of csrc/swe_dist.cuh restated in Python — one halo exchange
+    per stage with the lists of the C++ plan, one min all-reduce per step. It checks that the PLAN
+    (owned / halo / send / receive lists, CFL edge mask) gives bit-identical owned cells."""
+
+    STAGES = {0: [(0.0, 1.0, 1.0)], 1: [(0.0, 1.0, 1.0), (0.5, 0.5, 0.5)],
+              2: [(0.0, 1.0, 1.0), (0.75, 0.25, 0.25), (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0)]}
+
+    def __init__(self, plan, local):
+        self.plan, self.local = plan, local
+        self.nsend = sum(len(p[1]) for p in plan.peers)
+        self.nrecv = sum(len(p[2]) for p in plan.peers)
+        local.set_halo_lists(plan.send_list(), plan.recv_list())
+        local.set_cfl_edge_mask(plan.cfl_mask)
+        self.sendbuf = local.alloc(3 * max(self.nsend, 1))
+        self.recvbuf = local.alloc(3 * max(self.nrecv, 1))
+        self.exchanges = 0
+
+    def exchange(self):
+        import torch.distributed as dist
+        if not self.plan.peers:
+            return
+        self.local.pack(self.sendbuf)
+        ops, so, ro = [], 0, 0
+        for peer, s, r in self.plan.peers:
+            if len(s):
+                ops.append(dist.P2POp(dist.isend, self.sendbuf[3 * so:3 * (so + len(s))], peer))
+            if len(r):
+                ops.append(dist.P2POp(dist.irecv, self.recvbuf[3 * ro:3 * (ro + len(r))], peer))
+            so += len(s)
+            ro += len(r)
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.local.unpack(self.recvbuf)
+        self.exchanges += 1
+
+    def step(self, scheme, dt):
+        import torch.distributed as dist
+        L = self.local
+        stages = self.STAGES[scheme]
+        for k, (a0, a1, coef) in enumerate(stages):
+            L.compute_interface_values()
+            L.compute_fluxes()
+            if k == len(stages) - 1 and self.plan.world > 1:
+                dist.all_reduce(L.min_len_tensor(), op=dist.ReduceOp.MIN)
+            if k == 0 and len(stages) > 1:
+                L.save_state()
+            L.stage_update(a0, a1, coef, dt)
+            self.exchange()
+        L.advance_dt(dt)
+
+    def run(self, scheme, nsteps, dt, dt0=0.0):
+        if dt is None:
+            self.local.set_dt(dt0)
+        for _ in range(nsteps):
+            self.step(scheme, dt)

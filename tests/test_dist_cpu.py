@@ -1,5 +1,5 @@
-"""Multi-GPU host logic on CPU: world_size-2 (and 3) gloo jobs run the product's decomposition,
-halo exchange and dt min-reduction with the oracle as the local solver. The owned cells of all
+"""Multi-GPU host logic on CPU: world_size-2 (and 3) gloo jobs run the product's C++ decomposition
+plans (csrc/distplan.cpp) with a test-side exchange / dt min-reduction loop and the oracle as the local solver. The owned cells of all
 ranks must equal the undecomposed run BIT FOR BIT (reproducibility across GPU counts)."""
 import os
 import socket
@@ -60,53 +60,61 @@ def test_decomposed_run_is_bitwise_identical(tmp_path, world, mode, scheme, adap
     assert (seen == 1).all()  # every cell owned exactly once
 
 
-def test_strip_decomposition_lists_are_consistent():
-    """Rank r's receive list from r+1 addresses the same global cells, in the same order, as rank
-    r+1's send list to r; the CFL edge mask covers exactly the edges touching owned cells."""
+def test_strip_plans_are_consistent():
+    """Rank r's receive list from r+1 addresses the same global cells, in the same order, as rank r+1's
+    send list to r; every cell is owned exactly once; the CFL edge mask covers exactly the edges touching
+    owned cells; the ordering classes are what swe_dist's launch order relies on."""
     from swe_fvm_b200 import dist as swd
     n, world = 16, 4
-    decs = [swd.decompose_strips(n, n, 4.0 / n, r, world) for r in range(world)]
-    rows = swd.strip_rows(n, world)
-    offs = [max(rows[r][0] - swd.HALO_ROWS, 0) * 4 * n for r in range(world)]
-    assert sum(d.n_owned for d in decs) == 4 * n * n
+    plans = [swd.Plan.struct(r, world, n, n, 4.0 / n) for r in range(world)]
+    assert sum(p.n_owned for p in plans) == 4 * n * n
+    seen = np.zeros(4 * n * n, int)
+    for p in plans:
+        seen[p.global_cells[p.owned]] += 1
+    assert (seen == 1).all()
     for r in range(world - 1):
-        up = [p for p in decs[r].peers if p[0] == r + 1][0]
-        dn = [p for p in decs[r + 1].peers if p[0] == r][0]
-        np.testing.assert_array_equal(up[1] + offs[r], dn[2] + offs[r + 1])
-        np.testing.assert_array_equal(up[2] + offs[r], dn[1] + offs[r + 1])
-    d = decs[1]
-    mask = d.cfl_edge_mask().astype(bool)
-    et = d.mesh.edge_elements
-    touch = d.owned[et[:, 0]] | np.where(et[:, 1] >= 0, d.owned[np.maximum(et[:, 1], 0)], False)
-    np.testing.assert_array_equal(mask, touch)
+        up = [p for p in plans[r].peers if p[0] == r + 1][0]
+        dn = [p for p in plans[r + 1].peers if p[0] == r][0]
+        np.testing.assert_array_equal(plans[r].global_cells[up[1]], plans[r + 1].global_cells[dn[2]])
+        np.testing.assert_array_equal(plans[r].global_cells[up[2]], plans[r + 1].global_cells[dn[1]])
+    _check_plan_invariants(plans[1])
 
 
-def test_cell_classes_mark_halo_dependent_stencils():
-    """Class 1 = the cell or one of its three edge neighbours is a halo (received) cell; class 0
-    cells can therefore be reconstructed before the halo of the previous stage has arrived."""
+def _check_plan_invariants(p):
+    et, tt = p.mesh.edge_elements, p.mesh.element_neighbours
+    touch = p.owned[et[:, 0]] | np.where(et[:, 1] >= 0, p.owned[np.maximum(et[:, 1], 0)], False)
+    np.testing.assert_array_equal(p.cfl_mask.astype(bool), touch)
+    halo = np.zeros(p.mesh.nt, bool)
+    halo[p.recv_list()] = True
+    assert (~p.owned == halo).all()                       # every non-owned cell is received from some peer
+    sent = np.zeros(p.mesh.nt, bool)
+    sent[p.send_list()] = True
+    assert not (sent & ~p.owned).any()                    # only owned cells are sent
+    dep = np.array([any(j >= 0 and halo[j] for j in tt[i]) for i in range(p.mesh.nt)])
+    cls = p.classes
+    np.testing.assert_array_equal(cls == 3, halo)         # class 3: halo cells
+    np.testing.assert_array_equal(cls == 2, dep & ~halo)  # class 2: owned, stencil touches a halo cell
+    np.testing.assert_array_equal(cls == 1, sent & ~dep)  # class 1: sent, stencil free of halo cells
+    assert not ((cls == 2) & ~sent).any()                 # halo-dependent owned cells are always sent
+
+
+def test_general_plans_derive_send_lists_without_communication():
+    """Any mesh + partition vector: each rank derives its send lists by repeating the peers' ring growth, and
+    they pair up exactly with the peers' receive lists."""
     from swe_fvm_b200 import TriangMesh
     from swe_fvm_b200 import dist as swd
-    n, world = 12, 3
-    for r in range(world):
-        d = swd.decompose_strips(n, n, 4.0 / n, r, world)
-        cls = d.cell_classes()
-        halo = np.zeros(d.mesh.nt, bool)
-        halo[d.recv_list()] = True
-        tt = d.mesh.element_neighbours
-        for i in range(d.mesh.nt):
-            dep = halo[i] or any(j >= 0 and halo[j] for j in tt[i])
-            assert cls[i] == int(dep)
-        assert (~d.owned == halo).all()  # every non-owned cell is received from some peer
-        assert cls[d.owned].sum() > 0 and (cls == 0).sum() > 0
     bowl = TriangMesh.from_gmsh(os.path.join(GOLDEN, "bowl.msh"))
-    part = bowl.partition_rcb(2)
-    wants = []
-    for r in range(2):
-        sub = bowl.extract(part, r, swd.HALO_LAYERS)
-        gc, owner = np.array(sub.global_cells), np.array(sub.cell_owner)
-        wants.append({int(q): gc[owner == q] for q in np.unique(owner) if q != r})
-    for r in range(2):
-        d = swd.decompose_general(bowl, part, r, 2, all_gather_object=lambda w: wants)
-        cls = d.cell_classes()
-        assert set(np.nonzero(~d.owned)[0]) <= set(np.nonzero(cls == 1)[0])
-        assert 0 < cls.sum() < 0.2 * d.mesh.nt
+    world = 3
+    part = bowl.partition_rcb(world)
+    plans = [swd.Plan.from_mesh(r, world, bowl, part) for r in range(world)]
+    seen = np.zeros(bowl.nt, int)
+    for p in plans:
+        seen[p.global_cells[p.owned]] += 1
+        _check_plan_invariants(p)
+        assert 0 < (p.classes >= 2).sum() < 0.3 * p.mesh.nt
+    assert (seen == 1).all()
+    for r in range(world):
+        for peer, s, rcv in plans[r].peers:
+            back = [q for q in plans[peer].peers if q[0] == r][0]
+            np.testing.assert_array_equal(plans[r].global_cells[s], plans[peer].global_cells[back[2]])
+            np.testing.assert_array_equal(plans[r].global_cells[rcv], plans[peer].global_cells[back[1]])

@@ -127,10 +127,13 @@ def test_lake_at_rest_full_size_strip():
     assert np.abs(got[:, 0]).max() <= 1e-13
 
 
-def test_device_side_cases_match_host():
-    """§8 f2/f3: bathymetry + TriangAverage initial state + L2 error norm computed on the device
-    agree with the host path to round-off (device libm vs glibc), and the Thacker error after a
-    short run matches the host-evaluated norm."""
+def test_device_side_cases_match_the_oracle():
+    """§8 f2/f3: bathymetry + TriangAverage initial state computed on the device against the ORACLE's
+    restatement of examples/Tests.h + include/PointOperations.h:20-44 (oracle.OracleCase, itself pinned bit for
+    bit to upstream's TriangAverage in tests/test_ref_anchor.py), on a mesh the oracle generated itself.
+    Tolerance 1e-12 absolute on O(1) fields: the device's sin/cos/exp/atan differ from glibc in the last ulp
+    (floating-point tolerance, stated here); the product's HOST path must equal the oracle exactly."""
+    from oracle.oracle import OracleCase, OracleStructMesh
     from swe_fvm_b200 import Case, StructTriangMesh
     from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
     n = 96
@@ -143,7 +146,13 @@ def test_device_side_cases_match_host():
         dev = sd.GetVolField()
         case.set_bathymetry(mesh)
         host = case.initial_state(mesh, quad_n=6)
-        assert np.abs(dev - host).max() <= 1e-12, kind
+        omesh = OracleStructMesh(n, n, 4.0 / n)
+        ocase = OracleCase(kind, 2.0, 2.0, 4.0, level=case.c.level, amp=case.c.amp)
+        ocase.set_bathymetry(omesh)
+        want = ocase.initial_state(omesh, quad_n=6)
+        np.testing.assert_array_equal(mesh.geometry, omesh.geometry)
+        np.testing.assert_array_equal(host, want)
+        assert np.abs(dev - want).max() <= 1e-12, kind
     mesh, case, v0 = make_case("classic_thacker", n, quad_n=6)
     sd = SpaceDisc("hllc", "einfeldt", mesh, v0)
     td = TimeDisc(sd)

@@ -1,6 +1,11 @@
-"""Multi-GPU path on the device. (1) P partitions emulated on ONE GPU: P contexts stepped in
-lockstep with the product's pack/unpack kernels, CFL edge mask and device-resident dt — owned
-cells must equal the single-context run bit for bit. (2) With >= 2 GPUs: the real NCCL job."""
+"""Multi-GPU path on the device, through the swe_dist_* C-ABI (csrc/swe_dist.cuh).
+
+(1) swe_dist_group_create with every rank on ONE GPU: the complete transport runs for real — ordering
+    classes, class-split K1 / K4 launches, k_halo_pack_signal (stores + flag), k_halo_wait_unpack (spin on the
+    flags), the peer-memory CFL minimum (k_min_push / k_min_pull) — only the CUDA-IPC mapping is replaced by
+    direct pointers. Owned cells must equal the single-context run BIT FOR BIT, the order-independent
+    state hash and the final dt must agree.
+(2) With >= 2 GPUs: one process per GPU under torchrun (NCCL only as the bootstrap all-gather), CUDA IPC."""
 import os
 import socket
 import subprocess
@@ -13,118 +18,84 @@ from conftest import GOLDEN, ROOT, make_case
 
 pytestmark = pytest.mark.gpu
 
-STAGES = {0: [(0.0, 1.0, 1.0)], 1: [(0.0, 1.0, 1.0), (0.5, 0.5, 0.5)],
-          2: [(0.0, 1.0, 1.0), (0.75, 0.25, 0.25), (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0)]}
 
-
-def _emulate(decs, gids, case, scheme, nsteps, reorder):
-    """Lockstep emulation of DistributedSolver.step for all ranks inside one process."""
-    import torch
-    from swe_fvm_b200 import dist as swd
-    from swe_fvm_b200.solver import SpaceDisc
-    locs, sds, bufs = [], [], []
-    for d in decs:
-        case.set_bathymetry(d.mesh)
-        v0 = case.initial_state(d.mesh, quad_n=4)
-        sd = SpaceDisc("hllc", "einfeldt", d.mesh, v0, reorder=reorder)
-        L = swd.GpuLocal(sd)
-        L.set_cfl_edge_mask(d.cfl_edge_mask())
-        L.set_halo_lists(d.send_list(), d.recv_list())
-        ns, nr = len(d.send_list()), len(d.recv_list())
-        bufs.append((L.alloc(3 * max(ns, 1)), L.alloc(3 * max(nr, 1))))
-        L.set_dt(1e-3)
-        locs.append(L)
-        sds.append(sd)
-
-    def exchange():
-        for L, (sb, rb) in zip(locs, bufs):
-            L.pack(sb)
-        torch.cuda.synchronize()
-        for r, d in enumerate(decs):
-            ro = 0
-            for peer, s, rcv in d.peers:
-                # find my segment in the peer's send buffer
-                so = 0
-                for p2, s2, r2 in decs[peer].peers:
-                    if p2 == r:
-                        bufs[r][1][3 * ro:3 * (ro + len(rcv))] = bufs[peer][0][3 * so:3 * (so + len(s2))]
-                        assert len(s2) == len(rcv)
-                        np.testing.assert_array_equal(gids[peer][s2], gids[r][rcv])
-                        break
-                    so += len(s2)
-                ro += len(rcv)
-        for L, (sb, rb) in zip(locs, bufs):
-            L.unpack(rb)
-
-    for _ in range(nsteps):
-        st = STAGES[scheme]
-        for k, (a0, a1, coef) in enumerate(st):
-            for L in locs:
-                L.compute_interface_values()
-                L.compute_fluxes()
-            if k == len(st) - 1:  # global min all-reduce
-                mn = min(float(L.min_len_tensor().item()) for L in locs)
-                for L in locs:
-                    L.min_len_tensor().fill_(mn)
-            for L in locs:
-                if k == 0 and len(st) > 1:
-                    L.save_state()
-                L.stage_update(a0, a1, coef, None)
-            exchange()
-        for L in locs:
-            L.advance_dt(None)
-    out = []
-    for sd, d, g in zip(sds, decs, gids):
-        sd.synchronize()
-        out.append((g[d.owned], sd.GetVolField()[d.owned]))
-    return out
-
-
-def _single(mesh, v0, scheme, nsteps):
+def _single(mesh, v0, scheme, nsteps, dt=0.0, cor=0.0):
     from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
-    sd = SpaceDisc("hllc", "einfeldt", mesh, v0)
-    Solvers.run(TimeDisc(sd), scheme, nsteps, dt=0.0, dt0=1e-3)
-    return sd.GetVolField()
+    sd = SpaceDisc("hllc", "einfeldt", mesh, v0, cor=cor)
+    td = TimeDisc(sd)
+    Solvers.run(td, scheme, nsteps, dt=dt, dt0=1e-3)
+    sd.synchronize()
+    return sd.GetVolField(), sd.state_hash(), td.CFLdt()
 
 
-@pytest.mark.parametrize("world,scheme", [(2, 1), (4, 2)])
-def test_emulated_strips_bitwise(world, scheme):
+def _group_run(plans, case, scheme, nsteps, reorder, overlap, dt=0.0, cor=0.0):
+    from swe_fvm_b200 import dist as swd
+    v0s = []
+    for p in plans:
+        case.set_bathymetry(p.mesh)
+        v0s.append(case.initial_state(p.mesh, quad_n=4))
+    grp = swd.DistGroup(plans, [0] * len(plans), cor=cor, reorder=reorder, overlap=overlap, wait_timeout_s=20.0)
+    for sd, v0 in zip(grp.sds, v0s):
+        sd.SetVolField(v0)
+    grp.exchange()
+    grp.run(scheme, nsteps, dt=dt, dt0=1e-3)
+    grp.synchronize()
+    return grp
+
+
+@pytest.mark.parametrize("world,scheme,overlap,reorder", [(2, "ssprk2", True, True), (4, "ssprk3", True, False),
+                                                          (3, "euler", False, True), (2, "ssprk2", True, False)])
+def test_group_strips_on_one_gpu_bitwise(world, scheme, overlap, reorder):
     from swe_fvm_b200 import dist as swd
     n = 48
     mesh, case, v0 = make_case("classic_thacker", n, quad_n=4)
-    want = _single(mesh, v0, scheme, 30)
-    decs = [swd.decompose_strips(n, n, 4.0 / n, r, world) for r in range(world)]
-    gids = [np.arange(d.mesh.nt) + max(swd.strip_rows(n, world)[r][0] - swd.HALO_ROWS, 0) * 4 * n for r, d in enumerate(decs)]
+    want, want_hash, want_dt = _single(mesh, v0, scheme, 30, cor=0.2)
+    plans = [swd.Plan.struct(r, world, n, n, 4.0 / n) for r in range(world)]
+    grp = _group_run(plans, case, scheme, 30, reorder, overlap, cor=0.2)
     seen = np.zeros(mesh.nt, int)
-    for g, st in _emulate(decs, gids, case, scheme, 30, reorder=False):
+    for g, st in grp.owned_states():
         np.testing.assert_array_equal(st, want[g])
         seen[g] += 1
     assert (seen == 1).all()
+    assert grp.state_hash() == want_hash
+    for r in range(world):
+        assert grp.cfl_dt(r) == want_dt   # the peer-memory minimum is exact: same dt on every rank as on one GPU
+    grp.close()
 
 
-def test_emulated_rcb_partitions_bitwise_with_reordering():
+def test_group_rcb_partitions_on_one_gpu_bitwise():
     from swe_fvm_b200 import TriangMesh
     from swe_fvm_b200 import dist as swd
     bowl = TriangMesh.from_gmsh(os.path.join(GOLDEN, "bowl.msh"))
     mesh, case, v0 = make_case("bowl_hump", mesh=bowl, level=3.0, amp=0.5)
-    want = _single(mesh, v0, 1, 30)
+    want, want_hash, want_dt = _single(mesh, v0, "ssprk2", 30)
     world = 3
     part = bowl.partition_rcb(world)
-    wants = [None] * world
-    decs = []
-    # emulate all_gather_object: first pass collects every rank's wish list
-    for r in range(world):
-        sub = bowl.extract(part, r, swd.HALO_LAYERS)
-        gc, owner = np.array(sub.global_cells), np.array(sub.cell_owner)
-        wants[r] = {int(q): gc[owner == q] for q in np.unique(owner) if q != r}
-    for r in range(world):
-        decs.append(swd.decompose_general(bowl, part, r, world, all_gather_object=lambda w: wants))
-    gids = [np.array(d.global_cells) for d in decs]
+    plans = [swd.Plan.from_mesh(r, world, bowl, part) for r in range(world)]
+    grp = _group_run(plans, case, "ssprk2", 30, True, True)
     seen = np.zeros(mesh.nt, int)
-    for g, st in _emulate(decs, gids, case, 1, 30, reorder=True):
+    for g, st in grp.owned_states():
         np.testing.assert_array_equal(st, want[g])
         seen[g] += 1
     assert (seen == 1).all()
+    assert grp.state_hash() == want_hash and grp.cfl_dt(0) == want_dt
+    grp.close()
+
+
+def test_group_fixed_dt_steps_and_hash_detects_a_flipped_bit():
+    from swe_fvm_b200 import dist as swd
+    n = 32
+    mesh, case, v0 = make_case("classic_thacker", n, quad_n=4)
+    want, want_hash, _ = _single(mesh, v0, "ssprk2", 10, dt=2e-3)
+    plans = [swd.Plan.struct(r, 2, n, n, 4.0 / n) for r in range(2)]
+    grp = _group_run(plans, case, "ssprk2", 10, True, True, dt=2e-3)
+    assert grp.state_hash() == want_hash
+    st = grp.sds[0].GetVolField()
+    i = int(np.nonzero(plans[0].owned)[0][5])
+    st[i, 0] = np.nextafter(st[i, 0], np.inf)
+    grp.sds[0].SetVolField(st)
+    assert grp.state_hash() != want_hash
+    grp.close()
 
 
 def _free_port():
@@ -133,9 +104,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("transport", ["nccl", "p2p"])
 @pytest.mark.parametrize("mode", ["strips", "general"])
-def test_nccl_two_gpus_bitwise(tmp_path, mode, transport):
+def test_two_gpus_bitwise(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -143,17 +113,20 @@ def test_nccl_two_gpus_bitwise(tmp_path, mode, transport):
     out = str(tmp_path / "res")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_dist_worker_gpu.py"), mode, out, "30", "1", "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, SWE_HALO=transport))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     if mode == "strips":
         mesh, case, v0 = make_case("classic_thacker", 64, quad_n=4)
     else:
         bowl = TriangMesh.from_gmsh(os.path.join(GOLDEN, "bowl.msh"))
         mesh, case, v0 = make_case("bowl_hump", mesh=bowl, level=3.0, amp=0.5)
-    want = _single(mesh, v0, 1, 30)
+    want, want_hash, want_dt = _single(mesh, v0, "ssprk2", 30)
     seen = np.zeros(mesh.nt, int)
+    tot = 0
     for k in range(2):
         res = np.load(f"{out}.{k}.npz")
         np.testing.assert_array_equal(res["state"], want[res["gids"]])
         seen[res["gids"]] += 1
-    assert (seen == 1).all()
+        tot = (tot + int(res["hash"])) % (1 << 64)
+        assert float(res["dt"]) == want_dt
+    assert (seen == 1).all() and tot == want_hash
