@@ -123,7 +123,8 @@ SWE_API int swe_get_state_async(swe_ctx *ctx, double *prim_3xnt);
 SWE_API int swe_step(swe_ctx *ctx, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt);
 /* nsteps steps without host synchronisation. dt > 0: fixed dt. dt <= 0: adaptive, every
  * step uses dt = CFLdt() of the previous step's last stage (device-resident, no read-back);
- * the first adaptive step uses dt0. */
+ * the first adaptive step uses dt0, or with dt0 <= 0 the dt already stored on the device by the
+ * previous swe_run / swe_checkpoint_load (restart). */
 SWE_API int swe_run(swe_ctx *ctx, swe_scheme scheme, swe_flux flux, swe_wavespeed ws,
                     int64_t nsteps, double dt, double dt0);
 /* 0.15 * min(1, min over edges of length/wavespeed) of the last flux evaluation. */
@@ -167,6 +168,17 @@ SWE_API int swe_advance_dt(swe_ctx *ctx, int adaptive, double dt_fixed);
 /* keep the reconstructed edge-side w as well (needed only by swe_get_edge_states) and count branch hits. */
 SWE_API int swe_enable_taps(swe_ctx *ctx, int on);
 
+/* Flux registry: upstream's plug-in point (i), SpaceDisc::Fluxer (include/SpaceDisc.h:22). Fluxes are device
+ * functors registered at compile time (csrc/swe_flux_registry.cuh, csrc/user_fluxes.cuh: one functor + one line).
+ * Entries 0..5 are Fluxes::HLL/HLLC<Wavespeeds::Rusanov/Davis/Einfeldt> with id = 3 * swe_flux + swe_wavespeed;
+ * swe_set_fluxer(ctx, id) makes swe_step / swe_run / swe_compute_fluxes / swe_dist_* use that flux regardless
+ * of their (flux, wavespeed) arguments; id < 0 switches back. */
+SWE_API int32_t swe_fluxer_count(void);
+SWE_API const char *swe_fluxer_name(int32_t k);   /* k-th registry entry */
+SWE_API int32_t swe_fluxer_id(int32_t k);
+SWE_API int32_t swe_fluxer_find(const char *name); /* id, or -1 */
+SWE_API int swe_set_fluxer(swe_ctx *ctx, int32_t id);
+
 /* Switches for the places where upstream HEAD is unfinished. Defaults = the
  * repaired scheme; the alternatives reproduce upstream exactly as written and are bit-checked against
  * upstream's own sources compiled in oracle/_ref (tests/test_ref_anchor.py, tests/test_gpu_parity.py):
@@ -193,6 +205,24 @@ SWE_API int swe_get_fluxes(swe_ctx *ctx, double *f_3xne);
 SWE_API int swe_get_node_max_w(swe_ctx *ctx, double *maxw_nn);
 SWE_API int swe_get_draining_dt(swe_ctx *ctx, double *dti_nt);    /* of the last stage      */
 SWE_API int swe_get_cell_class(swe_ctx *ctx, int8_t *cls_nt);     /* 0 dry 1 part 2 full    */
+
+/* Per-cell accessors of the reference API, as whole-array taps (HOST buffers, caller numbering):
+ * swe_classify    <- MUSCLObject::IsDryCell / IsFullWetCell / IsPartWetCell (include/MUSCLObject.h:11-13) of the
+ *                    CURRENT state: 0 dry, 1 part-wet, 2 full-wet
+ * swe_compute_rhs <- TimeDisc::RHS(i, dt) for every i (include/TimeDisc.h:15, src/TimeDisc.cpp:3-41), 3 x nt,
+ *                    for the edge values / fluxes of the last swe_compute_interface_values + swe_compute_fluxes;
+ *                    also refreshes swe_get_draining_dt (TimeDisc::ComputeDrainingDt). Snapshot semantics (S7):
+ *                    every RHS sees the same state. The state itself is not changed. */
+SWE_API int swe_classify(swe_ctx *ctx, int8_t *cls_nt);
+SWE_API int swe_compute_rhs(swe_ctx *ctx, double dt, double *rhs_3xnt);
+SWE_API int swe_set_time(swe_ctx *ctx, double t);
+SWE_API int swe_get_dt(swe_ctx *ctx, double *dt); /* the device-resident dt of adaptive runs */
+
+/* Binary checkpoint / restart: state (caller numbering), simulated time, the device-resident dt and
+ * min_len_to_wavespeed (so an adaptive run continues bit-identically) and the solver settings, which must match
+ * on load (SWE_ERR_INVALID otherwise). A checkpoint can be loaded into a context with another device numbering. */
+SWE_API int swe_checkpoint_save(swe_ctx *ctx, const char *path);
+SWE_API int swe_checkpoint_load(swe_ctx *ctx, const char *path);
 
 /* Device reductions (diagnostics; the commented ComputeIntegrals of src/SpaceDisc.cpp:77-104):
  * out[0] = sum A_i h_i (mass), out[1] = sum A_i 0.5 h (u^2+v^2), out[2] = sum A_i (0.5 h^2 + h b),

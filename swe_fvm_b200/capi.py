@@ -104,6 +104,11 @@ SYMBOLS = {
     "swe_set_dt": (C.c_int, [_P, C.c_double]),
     "swe_advance_dt": (C.c_int, [_P, C.c_int, C.c_double]),
     "swe_enable_taps": (C.c_int, [_P, C.c_int]),
+    "swe_fluxer_count": (C.c_int32, []),
+    "swe_fluxer_name": (C.c_char_p, [C.c_int32]),
+    "swe_fluxer_id": (C.c_int32, [C.c_int32]),
+    "swe_fluxer_find": (C.c_int32, [C.c_char_p]),
+    "swe_set_fluxer": (C.c_int, [_P, C.c_int32]),
     "swe_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "swe_get_option": (C.c_int, [_P, C.c_char_p, _I32]),
     "swe_get_branch_counts": (C.c_int, [_P, _I64]),
@@ -113,6 +118,12 @@ SYMBOLS = {
     "swe_get_node_max_w": (C.c_int, [_P, _D]),
     "swe_get_draining_dt": (C.c_int, [_P, _D]),
     "swe_get_cell_class": (C.c_int, [_P, _I8]),
+    "swe_classify": (C.c_int, [_P, _I8]),
+    "swe_compute_rhs": (C.c_int, [_P, C.c_double, _D]),
+    "swe_set_time": (C.c_int, [_P, C.c_double]),
+    "swe_get_dt": (C.c_int, [_P, _D]),
+    "swe_checkpoint_save": (C.c_int, [_P, C.c_char_p]),
+    "swe_checkpoint_load": (C.c_int, [_P, C.c_char_p]),
     "swe_diagnostics": (C.c_int, [_P, _D]),
     "swe_set_cfl_edge_mask": (C.c_int, [_P, _U8]),
     "swe_halo_set_lists": (C.c_int, [_P, C.c_int64, _I64, C.c_int64, _I64]),

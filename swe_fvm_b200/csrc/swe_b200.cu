@@ -33,6 +33,7 @@ struct swe_ctx {
     bool reordered = false;
     bool taps = false;
     int opt_recon = 0, opt_pw2 = 0, opt_roe_fix = 0, opt_cfl_abs = 0;  // swe_set_option (semantic decisions S2/S3/S5/S6)
+    int fluxer = -1;    // registry id selected by swe_set_fluxer (-1: use the (flux, wavespeed) enums of the call)
     int opt_tiled = 0;  // K1 form: 0 = register-prefetched gathers (default, faster: profiles/r2_k1_tiled_vs_gather.md), 1 = TMA-staged tiles
     unsigned long long *dbg = nullptr;                                 // branch-hit counters (taps)
     int class_first[6] = {0, 0, 0, 0, 0, 0};  // device cell range of every ordering class
@@ -76,8 +77,9 @@ struct swe_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_pool;
 };
 
-enum { KT_RECONSTRUCT = 0, KT_PARTWET2, KT_FLUX, KT_DRAIN, KT_UPDATE, KT_COUNT };
-static const char *kt_names[KT_COUNT] = {"k_reconstruct", "k_partwet2", "k_flux", "k_drain", "k_update"};
+enum { KT_RECONSTRUCT = 0, KT_PARTWET2, KT_FLUX, KT_DRAIN, KT_UPDATE, KT_HALO_PACK, KT_HALO_WAIT, KT_MIN, KT_COUNT };
+static const char *kt_names[KT_COUNT] = {"k_reconstruct", "k_partwet2", "k_flux", "k_drain", "k_update",
+                                         "k_halo_pack_signal", "k_halo_wait_unpack", "k_min_push_pull"};
 constexpr size_t kKtMaxPairs = 8192;
 
 static inline int kt_begin(swe_ctx *c, int id) {
@@ -218,15 +220,32 @@ static int ensure_stage(swe_ctx *c, size_t n_doubles) {
     return SWE_OK;
 }
 
-template <int FLUX, bool OPT>
-static void launch_flux_ws(swe_ctx *c, const DevMesh &m, const DevFields &s, int ws) {
+// flux registry (swe_flux_registry.cuh): id -> kernel instantiation
+struct FluxerEntry { int id; const char *name; };
+static const FluxerEntry g_fluxers[] = {
+#define SWE_X(ID, NAME, TYPE) {ID, NAME},
+    SWE_FLUX_LIST(SWE_X)
+#undef SWE_X
+};
+constexpr int kNumFluxers = (int)(sizeof(g_fluxers) / sizeof(g_fluxers[0]));
+static bool fluxer_known(int id) {
+    for (int k = 0; k < kNumFluxers; ++k) if (g_fluxers[k].id == id) return true;
+    return false;
+}
+static void launch_flux(swe_ctx *c, const DevMesh &m, const DevFields &s, int fluxer_id) {
     const int g = std::min(nblk(c->ne, kBlock), c->sms * SWE_K2_GRID_PER_SM);
     const double ac = std::fabs(c->cor);
     const int rf = c->opt_roe_fix, ca = c->opt_cfl_abs;
-    switch (ws) {
-        case SWE_RUSANOV: k_flux<FLUX, WS_RUSANOV, OPT><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca); break;
-        case SWE_DAVIS: k_flux<FLUX, WS_DAVIS, OPT><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca); break;
-        default: k_flux<FLUX, WS_EINFELDT, OPT><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca); break;
+    const bool opt = rf || ca;  // the default instantiation is upstream as written
+    switch (fluxer_id) {
+#define SWE_X(ID, NAME, TYPE)                                                            \
+        case ID:                                                                         \
+            if (opt) k_flux<TYPE, true><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);   \
+            else k_flux<TYPE, false><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);      \
+            break;
+        SWE_FLUX_LIST(SWE_X)
+#undef SWE_X
+        default: break;
     }
 }
 
@@ -244,15 +263,16 @@ static void preload_kernels() {
     SWE_LOAD(k_reconstruct_tiled<T, 0>); SWE_LOAD(k_reconstruct_tiled<T, 1>); SWE_LOAD(k_reconstruct_tiled<T, 2>); \
     SWE_LOAD(k_reconstruct_slow<T>); SWE_LOAD(k_partwet2<T>)
     SWE_LOAD_K1(false); SWE_LOAD_K1(true);
-#define SWE_LOAD_K2(F, O) SWE_LOAD(k_flux<F, WS_RUSANOV, O>); SWE_LOAD(k_flux<F, WS_DAVIS, O>); SWE_LOAD(k_flux<F, WS_EINFELDT, O>)
-    SWE_LOAD_K2(FLUX_HLL, false); SWE_LOAD_K2(FLUX_HLL, true); SWE_LOAD_K2(FLUX_HLLC, false); SWE_LOAD_K2(FLUX_HLLC, true);
+#define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>);
+    SWE_FLUX_LIST(SWE_X)
+#undef SWE_X
     SWE_LOAD(k_drain);
     SWE_LOAD(k_update<true, true>); SWE_LOAD(k_update<true, false>); SWE_LOAD(k_update<false, true>); SWE_LOAD(k_update<false, false>);
+    SWE_LOAD(k_update<true, true, true>); SWE_LOAD(k_update<true, false, true>); SWE_LOAD(k_classify);
     SWE_LOAD(k_post_step); SWE_LOAD(k_set_scalar);
     SWE_LOAD(k_halo_pack); SWE_LOAD(k_halo_unpack); SWE_LOAD(k_halo_signal); SWE_LOAD(k_halo_wait);
     SWE_LOAD(k_halo_pack_signal); SWE_LOAD(k_halo_wait_unpack); SWE_LOAD(k_min_push); SWE_LOAD(k_min_pull);
     SWE_LOAD(k_state_hash); SWE_LOAD(k_state_in); SWE_LOAD(k_state_out); SWE_LOAD(k_diag_partial); SWE_LOAD(k_diag_final);
-#undef SWE_LOAD_K2
 #undef SWE_LOAD_K1
 #undef SWE_LOAD
     cudaGetLastError();
@@ -582,6 +602,22 @@ SWE_API int swe_enable_taps(swe_ctx *c, int on) {
     return SWE_OK;
 }
 
+// ---- flux registry ----
+SWE_API int32_t swe_fluxer_count(void) { return kNumFluxers; }
+SWE_API const char *swe_fluxer_name(int32_t k) { return (k >= 0 && k < kNumFluxers) ? g_fluxers[k].name : nullptr; }
+SWE_API int32_t swe_fluxer_id(int32_t k) { return (k >= 0 && k < kNumFluxers) ? g_fluxers[k].id : -1; }
+SWE_API int32_t swe_fluxer_find(const char *name) {
+    if (!name) return -1;
+    for (int k = 0; k < kNumFluxers; ++k) if (!std::strcmp(g_fluxers[k].name, name)) return g_fluxers[k].id;
+    return -1;
+}
+SWE_API int swe_set_fluxer(swe_ctx *c, int32_t id) {
+    if (!c) return SWE_ERR_INVALID;
+    if (id >= 0 && !fluxer_known(id)) { c->err = "swe_set_fluxer: no flux with this id is registered (csrc/swe_flux_registry.cuh)"; return SWE_ERR_INVALID; }
+    c->fluxer = id < 0 ? -1 : id;
+    return SWE_OK;
+}
+
 // Semantic-decision switches; every value is bit-checked against the same oracle option.
 SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     if (!c || !key) return SWE_ERR_INVALID;
@@ -695,17 +731,19 @@ SWE_API int swe_compute_interface_values_range(swe_ctx *c, int64_t first_cell, i
 
 SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {
     if (!c) return SWE_ERR_INVALID;
-    if ((flux != SWE_HLL && flux != SWE_HLLC) || ws < SWE_RUSANOV || ws > SWE_EINFELDT) {
-        c->err = "swe_compute_fluxes: unknown flux / wavespeed (registered: HLL, HLLC x Rusanov, Davis, Einfeldt)";
-        return SWE_ERR_INVALID;
+    int id = c->fluxer;  // swe_set_fluxer overrides the enum pair
+    if (id < 0) {
+        if ((flux != SWE_HLL && flux != SWE_HLLC) || ws < SWE_RUSANOV || ws > SWE_EINFELDT) {
+            c->err = "swe_compute_fluxes: unknown flux / wavespeed (built in: HLL, HLLC x Rusanov, Davis, Einfeldt; others via swe_set_fluxer)";
+            return SWE_ERR_INVALID;
+        }
+        id = 3 * (int)flux + (int)ws;
     }
     CUDA_TRY(c, cudaSetDevice(c->device));
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     const int kt = kt_begin(c, KT_FLUX);
-    const bool opt = c->opt_roe_fix || c->opt_cfl_abs;  // the default instantiation is upstream as written
-    if (flux == SWE_HLL) { if (opt) launch_flux_ws<FLUX_HLL, true>(c, m, s, ws); else launch_flux_ws<FLUX_HLL, false>(c, m, s, ws); }
-    else { if (opt) launch_flux_ws<FLUX_HLLC, true>(c, m, s, ws); else launch_flux_ws<FLUX_HLLC, false>(c, m, s, ws); }
+    launch_flux(c, m, s, id);
     kt_end(c, kt);
     return launch_check(c, "k_flux");
 }
@@ -788,6 +826,7 @@ SWE_API int swe_advance_dt(swe_ctx *c, int adaptive, double dt_fixed) {
     return launch_check(c, "k_post_step");
 }
 
+static int read_scalar_fwd(swe_ctx *c, int idx, double *v);
 static int one_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt, bool dev_dt) {
     int rc;
     auto upd = [&](double a0, double a1, double coef) {
@@ -821,9 +860,15 @@ SWE_API int swe_run(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed 
     if (!c) return SWE_ERR_INVALID;
     if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { c->err = "swe_run: unknown scheme"; return SWE_ERR_INVALID; }
     const bool adaptive = !(dt > 0.);
-    if (adaptive && !(dt0 > 0.)) { c->err = "swe_run: adaptive mode needs dt0 > 0"; return SWE_ERR_INVALID; }
     int rc;
-    if (adaptive && (rc = swe_set_dt(c, dt0))) return rc;
+    // adaptive, dt0 > 0: first step dt0; dt0 <= 0: continue with the dt already on the device (previous swe_run /
+    // swe_checkpoint_load), which makes a restarted adaptive run bit-identical to the uninterrupted one
+    if (adaptive && dt0 > 0. && (rc = swe_set_dt(c, dt0))) return rc;
+    if (adaptive && !(dt0 > 0.)) {
+        double cur = 0.;
+        if ((rc = read_scalar_fwd(c, 1, &cur))) return rc;
+        if (!(cur > 0.)) { c->err = "swe_run: adaptive mode needs dt0 > 0 (no dt stored on the device yet)"; return SWE_ERR_INVALID; }
+    }
     for (int64_t s = 0; s < nsteps; ++s) {
         if ((rc = one_step(c, scheme, flux, ws, dt, adaptive))) return rc;
         if ((rc = swe_advance_dt(c, adaptive ? 1 : 0, dt))) return rc;
@@ -838,7 +883,9 @@ static int read_scalar(swe_ctx *c, int idx, double *v) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return SWE_OK;
 }
+static int read_scalar_fwd(swe_ctx *c, int idx, double *v) { return read_scalar(c, idx, v); }
 SWE_API int swe_get_min_len_to_wavespeed(swe_ctx *c, double *v) { return read_scalar(c, 0, v); }
+SWE_API int swe_get_dt(swe_ctx *c, double *dt) { return read_scalar(c, 1, dt); }
 SWE_API int swe_cfl_dt(swe_ctx *c, double *dt) {
     double v = 0;
     int rc = read_scalar(c, 0, &v);
@@ -931,6 +978,110 @@ SWE_API int swe_diagnostics(swe_ctx *c, double out[6]) {
     if ((rc = launch_check(c, "k_diag_final"))) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(out, c->diag + 6 * kDiagBlocks, sizeof(double) * 6, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+
+// ---- per-cell accessors of the reference API (TimeDisc::RHS, MUSCLObject::Is*Cell) ----
+// Cell classes of the CURRENT state (0 dry, 1 part-wet, 2 full-wet), independent of the last reconstruction.
+SWE_API int swe_classify(swe_ctx *c, int8_t *out) {
+    if (!c || !out) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)3 * c->nt);
+    if (rc) return rc;
+    signed char *tmp = (signed char *)c->stage_aos, *tmp2 = tmp + c->nt;
+    k_classify<<<nblk(c->nt, 256), 256, 0, c->stream>>>(dev_mesh(c), c->cur[0], tmp);
+    if ((rc = launch_check(c, "k_classify"))) return rc;
+    k_cls_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, tmp, tmp2);
+    if ((rc = launch_check(c, "k_cls_out"))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(out, tmp2, (size_t)c->nt, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+// TimeDisc::RHS(i, dt) of every cell (src/TimeDisc.cpp:3-41) for the fluxes / edge values of the last
+// swe_compute_interface_values + swe_compute_fluxes and the current state: 3 x nt column-major, caller
+// numbering. Also refreshes the draining time steps (swe_get_draining_dt). The state is not changed.
+SWE_API int swe_compute_rhs(swe_ctx *c, double dt, double *rhs) {
+    if (!c || !rhs) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_stage(c, (size_t)6 * c->nt);
+    if (rc) return rc;
+    const DevMesh m = dev_mesh(c);
+    const DevFields s = dev_fields(c);
+    k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+    if ((rc = launch_check(c, "k_drain"))) return rc;
+    double *r0 = c->stage_aos, *r1 = r0 + c->nt, *r2 = r1 + c->nt, *aos = r2 + c->nt;
+    const int g = nblk(c->nt, kBlock);
+    if (c->cor != 0.) k_update<true, true, true><<<g, kBlock, 0, c->stream>>>(m, s, nullptr, nullptr, nullptr, r0, r1, r2, 0., 1., dt, 0., c->cor, 0, c->nt);
+    else k_update<true, false, true><<<g, kBlock, 0, c->stream>>>(m, s, nullptr, nullptr, nullptr, r0, r1, r2, 0., 1., dt, 0., c->cor, 0, c->nt);
+    if ((rc = launch_check(c, "k_update<rhs>"))) return rc;
+    k_state_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, r0, r1, r2, aos);
+    if ((rc = launch_check(c, "k_state_out"))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(rhs, aos, sizeof(double) * 3 * c->nt, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SWE_OK;
+}
+SWE_API int swe_set_time(swe_ctx *c, double t) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal + 2, t);
+    return launch_check(c, "k_set_scalar");
+}
+
+// ---- binary checkpoint / restart (upstream only has text dumps, examples/Main.cpp:65-73) ----
+// File: "SWEB200C" magic, version, nt, ne, nn, cor, time, dt, min_len_to_wavespeed, 4 option words, then the state
+// 3 x nt fp64 in the CALLER's numbering (so a checkpoint can be loaded into a context with another device numbering).
+namespace {
+struct CkptHeader {
+    char magic[8];
+    int32_t version, pad;
+    int64_t nt, ne, nn;
+    double cor, time, dt, min_len;
+    int32_t opt[4];
+};
+}  // namespace
+SWE_API int swe_checkpoint_save(swe_ctx *c, const char *path) {
+    if (!c || !path) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    std::vector<double> st((size_t)3 * c->nt);
+    int rc = swe_get_state(c, st.data());
+    if (rc) return rc;
+    double scal[4];
+    CUDA_TRY(c, cudaMemcpy(scal, c->scal, sizeof(scal), cudaMemcpyDeviceToHost));
+    CkptHeader h{};
+    std::memcpy(h.magic, "SWEB200C", 8);
+    h.version = 1; h.nt = c->nt; h.ne = c->ne; h.nn = c->nn; h.cor = c->cor;
+    h.min_len = scal[0]; h.dt = scal[1]; h.time = scal[2];
+    h.opt[0] = c->opt_recon; h.opt[1] = c->opt_pw2; h.opt[2] = c->opt_roe_fix; h.opt[3] = c->opt_cfl_abs;
+    FILE *f = std::fopen(path, "wb");
+    if (!f) { c->err = std::string("swe_checkpoint_save: cannot open ") + path; return SWE_ERR_IO; }
+    const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(st.data(), sizeof(double), st.size(), f) == st.size();
+    if (std::fclose(f) != 0 || !ok) { c->err = std::string("swe_checkpoint_save: short write to ") + path; return SWE_ERR_IO; }
+    return SWE_OK;
+}
+SWE_API int swe_checkpoint_load(swe_ctx *c, const char *path) {
+    if (!c || !path) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    FILE *f = std::fopen(path, "rb");
+    if (!f) { c->err = std::string("swe_checkpoint_load: cannot open ") + path; return SWE_ERR_IO; }
+    CkptHeader h{};
+    std::vector<double> st((size_t)3 * c->nt);
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "SWEB200C", 8) == 0 && h.version == 1;
+    if (ok && (h.nt != c->nt || h.ne != c->ne || h.nn != c->nn)) {
+        std::fclose(f);
+        c->err = "swe_checkpoint_load: the checkpoint belongs to a different mesh";
+        return SWE_ERR_INVALID;
+    }
+    ok = ok && std::fread(st.data(), sizeof(double), st.size(), f) == st.size();
+    std::fclose(f);
+    if (!ok) { c->err = std::string("swe_checkpoint_load: not a checkpoint / truncated: ") + path; return SWE_ERR_IO; }
+    if (h.cor != c->cor || h.opt[0] != c->opt_recon || h.opt[1] != c->opt_pw2 || h.opt[2] != c->opt_roe_fix || h.opt[3] != c->opt_cfl_abs) {
+        c->err = "swe_checkpoint_load: the checkpoint was written with other solver settings (cor / recon / pw2 / roe_fix / cfl_abs)";
+        return SWE_ERR_INVALID;
+    }
+    int rc = swe_set_state(c, st.data());  // resets the time, restored next
+    if (rc) return rc;
+    const double scal[3] = {h.min_len, h.dt, h.time};
+    CUDA_TRY(c, cudaMemcpy(c->scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
     return SWE_OK;
 }
 

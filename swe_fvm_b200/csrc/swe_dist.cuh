@@ -196,6 +196,7 @@ static int dist_push(swe_dist *d, double **buf) {  // pack-and-signal the state 
     if (d->peers.empty()) return SWE_OK;
     const int seq = ++d->seq;
     int rc, k = 0;
+    const int kt = kt_begin(c, KT_HALO_PACK);
     for (auto &q : d->peers) {
         const int g = std::max(1, nblk(q.send_count, 256));
         k_halo_pack_signal<<<g, 256, 0, c->stream>>>(q.send_count, c->send_cells + q.send_start, buf[0], buf[1], buf[2],
@@ -203,6 +204,7 @@ static int dist_push(swe_dist *d, double **buf) {  // pack-and-signal the state 
         if ((rc = launch_check(c, "k_halo_pack_signal"))) { d->err = c->err; return rc; }
         ++k;
     }
+    kt_end(c, kt);
     d->pending = true;
     return SWE_OK;
 }
@@ -211,8 +213,10 @@ static int dist_pull(swe_dist *d) {  // wait for every peer's flag, unpack into 
     if (!d->pending) return SWE_OK;
     d->pending = false;
     const int g = std::max(1, std::min(nblk(d->nrecv, 256), 4 * c->sms));
+    const int kt = kt_begin(c, KT_HALO_WAIT);  // includes the time spent waiting for a slower neighbour
     k_halo_wait_unpack<<<g, 256, 0, c->stream>>>(d->halo_flags(), (int)d->peers.size(), d->seq, d->timeout_cycles, c->flags + 5,
                                                  d->nrecv, c->recv_cells, d->recvbuf[d->seq & 1], c->cur[0], c->cur[1], c->cur[2]);
+    kt_end(c, kt);
     int rc = launch_check(c, "k_halo_wait_unpack");
     if (rc) d->err = c->err;
     return rc;
@@ -239,7 +243,9 @@ static int dist_stage(swe_dist *d, swe_flux flux, swe_wavespeed ws, double a0, d
     DIST_CTX(d, swe_compute_fluxes(c, flux, ws));
     if (last && world > 1) {  // this rank's CFL minimum to every rank's table (needed only by the next step's dt)
         const int seq = ++d->minseq;
+        const int kt = kt_begin(c, KT_MIN);
         k_min_push<<<1, 32, 0, c->stream>>>(c->scal, d->minpeers, world, d->plan->rank, seq);
+        kt_end(c, kt);
         if ((rc = launch_check(c, "k_min_push"))) { d->err = c->err; return rc; }
     }
     if (save) swe_save_state(c);
@@ -277,8 +283,10 @@ static int dist_one_step(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wave
             return rc;
     }
     if (d->plan->world > 1) {
+        const int kt = kt_begin(c, KT_MIN);
         k_min_pull<<<1, 32, 0, c->stream>>>(c->scal, d->min_table(), d->min_flags(), d->plan->world, d->minseq, d->timeout_cycles,
                                             c->flags + 5);
+        kt_end(c, kt);
         if ((rc = launch_check(c, "k_min_pull"))) { d->err = c->err; return rc; }
     }
     return SWE_OK;

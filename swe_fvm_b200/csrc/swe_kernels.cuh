@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "swe_device.cuh"
+#include "swe_flux_registry.cuh"
 
 namespace swe {
 
@@ -648,7 +649,7 @@ __device__ __forceinline__ double warp_min(double v) {
 #ifndef SWE_K2_MIN_BLOCKS
 #define SWE_K2_MIN_BLOCKS 8
 #endif
-template <int FLUX, int WS, bool OPT>
+template <class FLUXER, bool OPT>
 __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, DevFields s, double abscor, int roe_fix, int cfl_abs) {
     const int ne = m.ne;
     const int stride = gridDim.x * blockDim.x;
@@ -668,9 +669,9 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
                 elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
             } else {
                 double cand = 1.0;
-                riemann_flux<FLUX, WS, OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
-                                            __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand,
-                                            roe_fix, cfl_abs);
+                FLUXER::template eval<OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
+                                           __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand,
+                                           roe_fix, cfl_abs);
                 l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
             }
             st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
@@ -736,7 +737,8 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
 #ifndef SWE_K4_MIN_BLOCKS
 #define SWE_K4_MIN_BLOCKS 1
 #endif
-template <bool PLAIN, bool COR>
+// RHS_ONLY (tap for TimeDisc::RHS(i, dt)): store the increment (r0, r1, r2) instead of applying it.
+template <bool PLAIN, bool COR, bool RHS_ONLY = false>
 __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m, DevFields s, const double *__restrict__ w0,
                                                    const double *__restrict__ u0, const double *__restrict__ v0,
                                                    double *wout, double *uout, double *vout, double a0, double a1,
@@ -792,6 +794,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
         r1 += dtk * (nx * c_ek * (0.5 * h_ek * h_ek));
         r2 += dtk * (ny * c_ek * (0.5 * h_ek * h_ek));
     }
+    if (RHS_ONLY) { wout[i] = r0; uout[i] = r1; vout[i] = r2; return; }
     const double hc = wc - cb;
     double U0, U1, U2;
     if (PLAIN) {
@@ -814,6 +817,15 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     }
     if (!(isfinite(ow) && isfinite(ou) && isfinite(ov))) s.flags[0] = 1;
     wout[i] = ow; uout[i] = ou; vout[i] = ov;
+}
+
+// IsDryCell / IsFullWetCell / IsPartWetCell (src/MUSCLObject.cpp:13-29) of the CURRENT state, without reconstructing
+__global__ void k_classify(DevMesh m, const double *w, signed char *cls) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.nt) return;
+    const double4 G = m.cgeo[i];  // (cx, cy, cb, bfull): bfull = max node bed, +inf on boundary triangles
+    const double wi = w[i];
+    cls[i] = !is_wet(wi - G.z) ? 0 : ((G.w < wi) ? 2 : 1);
 }
 
 // after a step: time += dt_used; in adaptive mode dt = 0.15 * min_len (include/TimeDisc.h:13,22)

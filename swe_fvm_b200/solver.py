@@ -131,6 +131,19 @@ class SpaceDisc:
     BRANCHES = ("pw1_submerged", "pw1_cbrt", "pw1_bisection", "fw_dry_neighbour", "fw_partwet_neighbour", "fw_vertex_zeroed",
                 "fw_tvd_off", "pw2_to_pw1", "pw2_one_wet", "pw2_three_wet", "pw2_two_wet", "pw2_two_wet_fallback")
 
+    @staticmethod
+    def registered_fluxes() -> dict:
+        """{name: id} of the compile-time flux registry (csrc/swe_flux_registry.cuh)."""
+        l = capi.lib()
+        return {l.swe_fluxer_name(k).decode(): int(l.swe_fluxer_id(k)) for k in range(l.swe_fluxer_count())}
+
+    def set_fluxer(self, name_or_id):
+        """Select a registered flux by name or id for every following step (overrides flux / wavespeed)."""
+        fid = name_or_id if isinstance(name_or_id, int) else capi.lib().swe_fluxer_find(str(name_or_id).encode())
+        if fid < 0 and not isinstance(name_or_id, int):
+            raise KeyError(f"flux {name_or_id!r} is not registered: {sorted(self.registered_fluxes())}")
+        self._call("swe_set_fluxer", int(fid))
+
     def set_option(self, key: str, value: int):
         """Semantic-decision switches: recon (0 repaired | 1 as written | 2 first order), pw2, roe_fix, cfl_abs."""
         self._call("swe_set_option", key.encode(), int(value))
@@ -168,17 +181,34 @@ class SpaceDisc:
         self._call("swe_get_time", C.byref(v))
         return v.value
 
-    # -- checkpoint / restart (binary; the reference only has text dumps, examples/Main.cpp:65-73) --
+    # -- per-cell accessors of the reference API --
+    def classify(self) -> np.ndarray:
+        """IsDryCell / IsPartWetCell / IsFullWetCell of the current state: 0 / 1 / 2 per cell."""
+        return self._get("swe_classify", (self.nt,), dtype=np.int8)
+
+    def IsDryCell(self, i: int) -> bool:
+        return int(self.classify()[i]) == 0
+
+    def IsPartWetCell(self, i: int) -> bool:
+        return int(self.classify()[i]) == 1
+
+    def IsFullWetCell(self, i: int) -> bool:
+        return int(self.classify()[i]) == 2
+
+    def rhs(self, dt: float) -> np.ndarray:
+        """TimeDisc::RHS(i, dt) of every cell, (nt, 3), for the last interface values / fluxes."""
+        out = np.empty((self.nt, 3))
+        self._call("swe_compute_rhs", float(dt), capi.dptr(out))
+        return out
+
+    # -- checkpoint / restart (binary, in the C-ABI; the reference only has text dumps, examples/Main.cpp:65-73) --
     def save_checkpoint(self, path: str):
-        np.savez(path, state=self.GetVolField(), time=self.time(), nt=self.nt, cor=self.cor)
+        self._call("swe_checkpoint_save", str(path).encode())
 
     def load_checkpoint(self, path: str) -> float:
-        """Restores the state; returns the simulated time stored with it."""
-        with np.load(path) as z:
-            if int(z["nt"]) != self.nt:
-                raise ValueError("checkpoint belongs to a different mesh")
-            self.SetVolField(z["state"])
-            return float(z["time"])
+        """Restores state, time, dt and min_len_to_wavespeed; returns the simulated time stored with it."""
+        self._call("swe_checkpoint_load", str(path).encode())
+        return self.time()
 
     def kernel_timing(self, enable: bool = True):
         self._call("swe_kernel_timing", int(enable))
@@ -223,6 +253,13 @@ class TimeDisc:
         v = C.c_double()
         self._sd._call("swe_cfl_dt", C.byref(v))
         return v.value
+
+    def RHS(self, i: int, dt: float) -> np.ndarray:
+        """TimeDisc::RHS(i, dt) (include/TimeDisc.h:15); whole-array form: sd.rhs(dt)."""
+        return self._sd.rhs(dt)[i]
+
+    def ComputeDrainingDt(self, i: int) -> float:
+        return float(self._sd.draining_dt()[i]) if i >= 0 else float("inf")
 
 
 class Solvers:

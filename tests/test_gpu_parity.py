@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 SCHEMES = {"euler": 0, "ssprk2": 1, "ssprk3": 2}
 
 
-def _pair(mesh, v0, flux="hllc", ws="einfeldt", cor=0.0, reorder=False, taps=True):
+def _pair(mesh, v0, flux="hllc", ws="einfeldt", cor=0.0, reorder=False, taps=True):  # noqa: D103
     from swe_fvm_b200.solver import SpaceDisc, TimeDisc
     from oracle.oracle import Oracle
     sd = SpaceDisc(flux, ws, mesh, v0, cor=cor, reorder=reorder, taps=taps)
@@ -190,6 +190,61 @@ def test_golden_step_out1_on_the_gpu():
         np.testing.assert_array_equal(q, r.get_state())
 
 
+def test_flux_registry_builtin_ids_and_a_user_flux(cases):
+    """Plug-in point (i): fluxes are device functors in a compile-time registry. Selecting a built-in flux by
+    registry id equals the enum path bit for bit; the sample user flux (csrc/user_fluxes.cuh, Local
+    Lax-Friedrichs) is reachable by name and equals its numpy restatement on the same edge states."""
+    from oracle.oracle import Oracle
+    from swe_fvm_b200 import SweError
+    from swe_fvm_b200.solver import SpaceDisc
+    regs = SpaceDisc.registered_fluxes()
+    assert regs["HLL<Rusanov>"] == 0 and regs["HLLC<Einfeldt>"] == 5 and "LocalLaxFriedrichs" in regs
+    mesh, case, v0 = cases["thacker64"]
+    sd = SpaceDisc("hll", "rusanov", mesh, v0, cor=0.3, taps=True)
+    ref = Oracle(mesh, cor=0.3)
+    ref.set_state(v0)
+    sd.ComputeInterfaceValues()
+    ref.compute_interface_values()
+    sd.set_fluxer(regs["HLLC<Davis>"])       # overrides the ("hll", "rusanov") of the constructor
+    sd.ComputeFluxes()
+    ref.compute_fluxes(1, 1)
+    np.testing.assert_array_equal(sd.GetFluxes(), ref.fluxes())
+    assert sd.GetMinLenToWavespeed() == ref.min_len_to_wavespeed()
+    sd.set_fluxer("LocalLaxFriedrichs")
+    sd.ComputeFluxes()
+    got, edg = sd.GetFluxes(), sd.GetEdgField()
+    g = ref.geometry()
+    et = mesh.edge_elements
+    inner = np.nonzero(et[:, 1] >= 0)[0]
+    lf, lt = et[inner, 0], et[inner, 1]
+    L, R = edg[2 * inner + (lf < lt)], edg[2 * inner + (lt < lf)]
+    be, n = g["E"][inner, 2], g["n0"][inner]
+    hl, hr = L[:, 0] - be, R[:, 0] - be
+    ul, ur = L[:, 1] * n[:, 0] + L[:, 2] * n[:, 1], R[:, 1] * n[:, 0] + R[:, 2] * n[:, 1]
+    a = np.maximum(np.abs(ul) + np.sqrt(hl), np.abs(ur) + np.sqrt(hr))
+
+    def elem(h, hu, hv):
+        q = hu * n[:, 0] + hv * n[:, 1]
+        wet = h > 1e-12
+        hs = np.where(wet, h, 1.0)
+        return np.where(wet, q, 0.0), np.where(wet, (q / hs) * hu + (0.5 * h * h) * n[:, 0], 0.0), np.where(wet, (q / hs) * hv + (0.5 * h * h) * n[:, 1], 0.0)
+
+    Fl, Fr = elem(hl, hl * L[:, 1], hl * L[:, 2]), elem(hr, hr * R[:, 1], hr * R[:, 2])
+    live = (hl + hr > 1e-10) & (a > 1e-10)
+    for c, (ql, qr) in enumerate(((hl, hr), (hl * L[:, 1], hr * R[:, 1]), (hl * L[:, 2], hr * R[:, 2]))):
+        want = np.where(live, 0.5 * (Fl[c] + Fr[c]) - 0.5 * a * (qr - ql), 0.0)
+        np.testing.assert_allclose(got[inner, c], want, rtol=0, atol=1e-15)
+    assert live.sum() > 100
+    with pytest.raises(KeyError):
+        sd.set_fluxer("NoSuchFlux")
+    with pytest.raises(SweError):
+        sd.set_fluxer(99)
+    sd.set_fluxer(-1)                        # back to the constructor's enums
+    sd.ComputeFluxes()
+    ref.compute_fluxes(0, 0)
+    np.testing.assert_array_equal(sd.GetFluxes(), ref.fluxes())
+
+
 def test_create_rejects_another_local_edge_order():
     """swe_create validates the local convention the kernels rely on (edge k joins nodes k, k+1; neighbour k across it)."""
     from swe_fvm_b200 import StructTriangMesh, SweError
@@ -265,12 +320,74 @@ def test_checkpoint_restart_is_exact(cases, tmp_path):
     straight = sd.GetVolField()
     sd.SetVolField(v0)
     Solvers.run(td, "ssprk2", 15, dt=2e-3)
-    sd.save_checkpoint(str(tmp_path / "ck.npz"))
+    sd.save_checkpoint(str(tmp_path / "ck.bin"))
     sd2, td2, _ = _pair(mesh, v0, reorder=True, taps=False)
-    t = sd2.load_checkpoint(str(tmp_path / "ck.npz"))
+    t = sd2.load_checkpoint(str(tmp_path / "ck.bin"))
     assert abs(t - 15 * 2e-3) < 1e-15
     Solvers.run(td2, "ssprk2", 25, dt=2e-3)
     np.testing.assert_array_equal(sd2.GetVolField(), straight)
+    assert abs(sd2.time() - 40 * 2e-3) < 1e-14
+
+
+def test_adaptive_restart_is_bit_identical(cases, tmp_path):
+    """swe_checkpoint_save / _load (C-ABI) keep time, the device-resident dt and min_len: an adaptive run that
+    is interrupted, written to disk and continued in ANOTHER context (other device numbering) equals the
+    uninterrupted run bit for bit; a checkpoint of another mesh / other settings is refused."""
+    from swe_fvm_b200 import SweError
+    from swe_fvm_b200.solver import Solvers
+    mesh, case, v0 = cases["thacker64"]
+    sd, td, _ = _pair(mesh, v0, taps=False, cor=0.2)
+    Solvers.run(td, "ssprk2", 40, dt=0.0, dt0=1e-3)
+    straight, t_straight = sd.GetVolField(), sd.time()
+    sd.SetVolField(v0)
+    Solvers.run(td, "ssprk2", 17, dt=0.0, dt0=1e-3)
+    sd.save_checkpoint(str(tmp_path / "ck.bin"))
+    sd2, td2, _ = _pair(mesh, v0, reorder=True, taps=False, cor=0.2)
+    sd2.load_checkpoint(str(tmp_path / "ck.bin"))
+    Solvers.run(td2, "ssprk2", 23, dt=0.0, dt0=0.0)   # dt0 <= 0: continue with the restored dt
+    np.testing.assert_array_equal(sd2.GetVolField(), straight)
+    assert sd2.time() == t_straight
+    sd3, _, _ = _pair(mesh, v0, taps=False, cor=0.0)      # other Coriolis parameter
+    with pytest.raises(SweError):
+        sd3.load_checkpoint(str(tmp_path / "ck.bin"))
+    other, _, v1 = cases["wet48"]
+    sd4, _, _ = _pair(other, v1, taps=False, cor=0.2)     # other mesh
+    with pytest.raises(SweError):
+        sd4.load_checkpoint(str(tmp_path / "ck.bin"))
+    with pytest.raises(SweError):
+        sd4.load_checkpoint(str(tmp_path / "missing.bin"))
+
+
+def test_reference_style_time_loop_with_rhs_and_cell_classes(cases):
+    """The reference's own loop shape, `cons(i) += td->RHS(i, dt)` (src/Solvers.cpp:11-13), expressed with the
+    per-cell accessors: RHS(i, dt) and Is*Cell(i) are whole-array taps of the device. One Euler step assembled
+    on the host from sd.rhs(dt) through the oracle's ConsAssigner equals swe_step bit for bit."""
+    from oracle.oracle import Oracle
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    mesh, case, v0 = cases["thacker64"]
+    sd, td, ref = _pair(mesh, v0, cor=0.3)
+    for _ in range(3):
+        Solvers.SSPRK2(td, 2e-3)
+        ref.step(1, 1, 2, 2e-3)
+    np.testing.assert_array_equal(sd.classify(), ref.cell_class())
+    i_dry, i_pw, i_fw = (int(np.nonzero(ref.cell_class() == k)[0][0]) for k in (0, 1, 2))
+    assert sd.IsDryCell(i_dry) and sd.IsPartWetCell(i_pw) and sd.IsFullWetCell(i_fw)
+    sd.ComputeInterfaceValues(); sd.ComputeFluxes()
+    ref.compute_interface_values(); ref.compute_fluxes(1, 2)
+    dt = 3e-3
+    rhs = sd.rhs(dt)
+    want = np.array([ref.rhs(i, dt) for i in range(0, mesh.nt, 37)])
+    np.testing.assert_array_equal(rhs[::37], want)
+    np.testing.assert_array_equal(sd.draining_dt(), ref.draining_dt_live())
+    assert td.RHS(i_fw, dt).tolist() == rhs[i_fw].tolist() and td.ComputeDrainingDt(-1) == float("inf")
+    # host-side Euler step from the taps (ConsAssigner += RHS), then the device's own step
+    state = sd.GetVolField()
+    o2 = Oracle(mesh, cor=0.3)
+    o2.set_state(state)
+    for i in range(mesh.nt):
+        o2.assign_cons(i, o2.get_cons(i) + rhs[i])
+    Solvers.Euler(td, dt)
+    np.testing.assert_array_equal(sd.GetVolField(), o2.get_state())
 
 
 @pytest.mark.parametrize("ni,nj", [(1, 1), (2, 1), (3, 3)])
