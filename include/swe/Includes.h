@@ -24,6 +24,7 @@ struct Array : std::array<double, k> {  // upstream: Eigen::Array<double, k, 1>
     friend Array operator-(Array a, const Array &b) { return a -= b; }
     friend Array operator*(double s, Array a) { return a *= s; }
     friend Array operator*(Array a, double s) { return a *= s; }
+    friend Array operator/(Array a, double s) { for (size_t i = 0; i < k; ++i) a[i] /= s; return a; }
 };
 
 // upstream: Eigen::Array<double, k, Dynamic>, column-major => column i is contiguous

@@ -419,6 +419,7 @@ SWE_API int swe_case_initial_state_device(swe_ctx *ctx, const swe_case *c, int32
 SWE_API int swe_case_l2_error(swe_ctx *ctx, const swe_case *c, double t, double out[3]);
 
 SWE_API const char *swe_version(void);
+SWE_API int32_t swe_device_count(void); /* CUDA devices visible to this process (0 without a GPU) */
 
 #ifdef __cplusplus
 }

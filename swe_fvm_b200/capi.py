@@ -182,6 +182,7 @@ SYMBOLS = {
     "swe_case_initial_state_device": (C.c_int, [_P, C.POINTER(CaseStruct), C.c_int32, C.c_double]),
     "swe_case_l2_error": (C.c_int, [_P, C.POINTER(CaseStruct), C.c_double, _D]),
     "swe_version": (C.c_char_p, []),
+    "swe_device_count": (C.c_int32, []),
 }
 
 _lib = None

@@ -280,7 +280,12 @@ static void preload_kernels() {
 
 extern "C" {
 
-SWE_API const char *swe_version(void) { return "swe_b200 0.1 (sm_100a, fp64, -fmad=false)"; }
+SWE_API const char *swe_version(void) { return "swe_b200 0.2 (sm_100a, fp64, -fmad=false)"; }
+SWE_API int32_t swe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 SWE_API const char *swe_last_error(const swe_ctx *ctx) {
     if (ctx) return ctx->err.c_str();

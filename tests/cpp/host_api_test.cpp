@@ -107,11 +107,82 @@ int main(int argc, char **argv) {
         LakeAtRestTest l2(parser, dimer, 2., 2.);
         CHECK(l2.b(2., 2.) == -0.2);
     }
+    // the virtual Test hierarchy: built-in cases agree with their C / device description, and a USER-DEFINED case
+    // (deriving from BowlTest, like upstream's BallTest would) plugs into SetBathymetry / InitialState
+    {
+        ClassicThackerTest ct(2., 2., 0.3, 0., 1., 0.5, 0.1, 0.4);
+        const swe_case *cc = ct.Builtin();
+        CHECK(cc != nullptr);
+        for (double x : {1.6, 2.0, 2.35})
+            for (double t : {0., 0.2, 0.7}) {
+                double o[4];
+                swe_case_eval(cc, x, 2.2, t, o);
+                CHECK(std::fabs(ct.b(x, 2.2) - o[0]) < 1e-15 && std::fabs(ct.h(x, 2.2, t) - o[1]) < 1e-15);
+                CHECK(std::fabs(ct.u(x, 2.2, t) - o[2]) < 1e-15 && std::fabs(ct.v(x, 2.2, t) - o[3]) < 1e-15);
+            }
+        const Test &base = ct;  // through the abstract interface, as upstream's drivers use it
+        CHECK(base.w(2., 2., 0.) == base.h(2., 2., 0.) + base.b(2., 2.) && base.IsWet(2., 2., 0.) && !base.IsWet(0.1, 0.1, 0.));
+        struct TiltedPool : BowlTest {  // user case: paraboloid bed, tilted free surface, solid-body rotation
+            TiltedPool() : BowlTest(2., 2., 0., 0., 1.) {}
+            double u(double, double y, double) const override { return -0.1 * (y - m_mid_y); }
+            double v(double x, double, double) const override { return 0.1 * (x - m_mid_x); }
+            double h(double x, double y, double) const override { return std::max(0., -0.5 + 0.05 * (x - m_mid_x) - b(x, y)); }
+        } pool;
+        CHECK(pool.Builtin() == nullptr);
+        Domain pd{StructTriangMesh{12, 12, 4. / 12}};
+        pool.SetBathymetry(pd);
+        CHECK(pd.AtNode(0) == pool.b(0., 0.));
+        const VolumeField p0 = pool.InitialState(pd, 3);
+        Idx wet = 0, dry = 0;
+        for (Idx t = 0; t < pd.Mesh().NumTriangles(); ++t) {
+            const Point c = pd.T(t);
+            if (p0.h(t) > 0.05) { ++wet; CHECK(std::fabs(p0.w(t) - (-0.5 + 0.05 * (c[0] - 2.))) < 0.05); }
+            else if (p0.h(t) == 0.) { ++dry; CHECK(p0.u(t) == 0. && p0.v(t) == 0.); }
+        }
+        CHECK(wet > 20 && dry > 100);
+        // the built-in path and the generic virtual path give the same initial state for a built-in case
+        struct ThackerViaVirtuals : ClassicThackerTest {
+            using ClassicThackerTest::ClassicThackerTest;
+            const swe_case *Builtin() const override { return nullptr; }
+        } tv(2., 2.);
+        ClassicThackerTest tb(2., 2.);
+        Domain td1{StructTriangMesh{10, 10, 0.4}};
+        tb.SetBathymetry(td1);
+        const VolumeField a0 = tb.InitialState(td1, 4, 0.1), a1 = tv.InitialState(td1, 4, 0.1);
+        for (Idx t = 0; t < td1.Mesh().NumTriangles(); ++t)
+            CHECK(std::fabs(a0.w(t) - a1.w(t)) < 1e-14 && std::fabs(a0.u(t) - a1.u(t)) < 1e-14 && std::fabs(a0.v(t) - a1.v(t)) < 1e-14);
+    }
+    // PointOperations.h mirror (upstream include/PointOperations.h:8-51, include/CubicPolyMath.h)
+    {
+        const Point a{0., 0., 1.}, b{3., 4., 2.}, c{0., 2., 5.};
+        CHECK(Len(a, b) == 5. && Det(b, c) == 6. && TriangArea(a, b, c) == 3.);
+        const Point x = Intersection(Point{0., 0., 0.}, Point{2., 2., 0.}, Point{2., 0., 0.}, Point{0., 2., 0.});  // den > 0 (S10d)
+        CHECK(std::fabs(x[0] - 1.) < 1e-15 && std::fabs(x[1] - 1.) < 1e-15);
+        bool par = false;
+        try { Intersection(a, b, a, b); } catch (const SolverError &) { par = true; }
+        CHECK(par);
+        const auto g = Gradient(Point{0., 0., 1.}, Point{1., 0., 3.}, Point{0., 1., 0.5});  // z = 1 + 2x - 0.5y
+        CHECK(std::fabs(g[0] - 2.) < 1e-15 && std::fabs(g[1] + 0.5) < 1e-15);
+        const auto gp = Gradient(Point{0., 0., 1.}, Point{1e-9, 1., 0.5 + 2e-9}, Point{1., 0., 3.});  // pivoting path
+        CHECK(std::fabs(gp[0] - 2.) < 1e-12 && std::fabs(gp[1] + 0.5) < 1e-12);
+        CHECK(std::fabs(Bisection(CubicPoly(-0.5), 0., 1.) - std::cbrt(0.5)) < 1e-15);
+        CHECK(Bisection(CubicPoly(1.), 0., 1.) == 0.);  // same sign at both ends: the end with the smaller |f|
+        const std::function<Array<2>(const Point &)> lin = [](const Point &q) { return Array<2>{1. + 2. * q[0] - q[1], q[2]}; };
+        const Array<2> avg = TriangAverage<2, 7>(a, b, c, lin);  // exact for linear integrands: value at the centroid
+        CHECK(std::fabs(avg[0] - (1. + 2. * 1. - 2.)) < 1e-13 && std::fabs(avg[1] - 8. / 3.) < 1e-13);
+    }
     // flux tags keep the reference's spelling
     constexpr Fluxer f = Fluxes::HLLC<Wavespeeds::Einfeldt>;
     static_assert(f.flux == SWE_HLLC && f.wavespeed == SWE_EINFELDT, "tag mapping");
     constexpr Fluxer f2 = Fluxes::HLL<Wavespeeds::Rusanov>;
     static_assert(f2.flux == SWE_HLL && f2.wavespeed == SWE_RUSANOV, "tag mapping");
+    CHECK(f.RegistryId() == 5 && f2.RegistryId() == 0);
+    CHECK(swe_fluxer_count() >= 7 && swe_fluxer_find("HLLC<Einfeldt>") == 5);
+    const Fluxer llf = Fluxes::Registered("LocalLaxFriedrichs");  // a flux added through csrc/user_fluxes.cuh
+    CHECK(llf.id == 6 && llf.RegistryId() == 6);
+    bool nof = false;
+    try { Fluxes::Registered("NoSuchFlux"); } catch (const DomainError &) { nof = true; }
+    CHECK(nof);
     std::printf("%s (%d failed checks)\n", fails ? "FAILED" : "ok", fails);
     return fails ? 1 : 0;
 }

@@ -33,7 +33,7 @@ def test_cpp_driver_reproduces_reference_dumps(tmp_path):
     out0.dat equals the reference's out0.dat, out1.dat equals the Python/C-ABI path at print
     precision; lake at rest and Thacker drivers run and report sane numbers."""
     _build()
-    r = subprocess.run([EXE, os.path.join(GOLDEN, "bowl.msh")], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([EXE, os.path.join(GOLDEN, "bowl.msh"), "--gpus", "3"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     with gzip.open(os.path.join(GOLDEN, "topology.dat.gz"), "rt") as f:
         assert f.read() == open(tmp_path / "topology.dat").read()
@@ -54,8 +54,31 @@ def test_cpp_driver_reproduces_reference_dumps(tmp_path):
     lines = r.stdout.splitlines()
     lake = [l for l in lines if l.startswith("TestLakeAtRest")][0]
     assert float(lake.split("max|u|,|v| = ")[1].split(",")[0]) < 1e-14
-    th = [l for l in lines if l.startswith("TestThacker")][0]
+    th = [l for l in lines if l.startswith("TestThacker n=")][0]
     assert float(th.split("L2 error of h = ")[1].split(",")[0]) < 2e-2
+    # a time loop in upstream's own style (cons(i) += td->RHS(i, dt)) equals Solvers::Euler on the device
+    loop = [l for l in lines if l.startswith("TestReferenceStyleLoop")][0]
+    assert float(loop.split("max diff to Solvers::Euler = ")[1].split(";")[0]) == 0.0
+    # the same SpaceDisc / Solvers calls on 3 ranks (RCB partition, peer-memory halo exchange): bit-identical
+    multi = [l for l in lines if l.startswith("TestThackerMultiGpu")][0]
+    assert " 0 cells differ" in multi
+    a, b = multi.split("CFLdt ")[1].split(" vs ")
+    assert float(a) == float(b)
+
+
+@pytest.mark.gpu
+def test_cpp_config4_driver_is_gpu_count_invariant(tmp_path):
+    """examples/Main.cpp --config4 n: the structured-strips multi-GPU driver (configs[4] at n = 8192) at a small n:
+    the state hash after 10 adaptive steps is the same for 1, 2 and 4 ranks."""
+    _build()
+    hashes, dts = [], []
+    for g in (1, 2, 4):
+        r = subprocess.run([EXE, "--config4", "192", "10", "--gpus", str(g)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        line = [l for l in r.stdout.splitlines() if l.startswith("TestConfig4")][0]
+        hashes.append(line.split("state hash = ")[1].strip())
+        dts.append(line.split("CFLdt = ")[1].split(",")[0])
+    assert len(set(hashes)) == 1 and len(set(dts)) == 1, (hashes, dts)
 
 
 def test_cpp_host_api_without_gpu(tmp_path):
