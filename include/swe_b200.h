@@ -119,6 +119,15 @@ SWE_API int swe_get_state(swe_ctx *ctx, double *prim_3xnt);
 SWE_API int swe_set_state_async(swe_ctx *ctx, const double *prim_3xnt);
 SWE_API int swe_get_state_async(swe_ctx *ctx, double *prim_3xnt);
 
+/* Host-buffer pipeline: a stream of independent states (ensemble members, batches), one time step each. Each call
+ * enqueues upload of host_in (3 x nt, should be pinned) -> one step of size dt -> download into host_out and returns
+ * at once; the upload of the next batch and the download of the previous one overlap the step of the current one
+ * (three streams, double-buffered staging: steady-state cost per batch = max(H2D, step, D2H)). swe_wait_host blocks
+ * until every submitted batch has landed in its host_out (and reports SWE_ERR_NUMERIC like swe_synchronize). */
+SWE_API int swe_submit_step_host(swe_ctx *ctx, const double *host_in_3xnt, double *host_out_3xnt, swe_scheme scheme,
+                                 swe_flux flux, swe_wavespeed ws, double dt);
+SWE_API int swe_wait_host(swe_ctx *ctx);
+
 /* One time step of the chosen scheme with a fixed dt (like every reference driver). */
 SWE_API int swe_step(swe_ctx *ctx, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt);
 /* nsteps steps without host synchronisation. dt > 0: fixed dt. dt <= 0: adaptive, every
@@ -364,6 +373,10 @@ SWE_API int swe_dist_run(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wave
 /* group form: issues every step for all ranks of one process in turn */
 SWE_API int swe_dist_group_run(swe_dist **ranks, int32_t world, swe_scheme scheme, swe_flux flux, swe_wavespeed ws,
                                int64_t nsteps, double dt, double dt0);
+/* the host-buffer pipeline of swe_submit_step_host on a rank: LOCAL state (owned + halo cells) in and out */
+SWE_API int swe_dist_submit_step_host(swe_dist *d, const double *host_in_3xntlocal, double *host_out_3xntlocal,
+                                      swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt);
+SWE_API int swe_dist_wait_host(swe_dist *d);
 /* waits for the rank's stream; SWE_ERR_NUMERIC on a non-finite state, SWE_ERR_CUDA if a peer wait timed out */
 SWE_API int swe_dist_synchronize(swe_dist *d);
 SWE_API int swe_dist_cfl_dt(swe_dist *d, double *dt);     /* 0.15 * global min (after a step)               */

@@ -86,6 +86,10 @@ SYMBOLS = {
     "swe_get_state": (C.c_int, [_P, _D]),
     "swe_set_state_async": (C.c_int, [_P, _D]),
     "swe_get_state_async": (C.c_int, [_P, _D]),
+    "swe_submit_step_host": (C.c_int, [_P, _D, _D, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "swe_wait_host": (C.c_int, [_P]),
+    "swe_dist_submit_step_host": (C.c_int, [_P, _D, _D, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "swe_dist_wait_host": (C.c_int, [_P]),
     "swe_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double]),
     "swe_run": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double]),
     "swe_cfl_dt": (C.c_int, [_P, _D]),

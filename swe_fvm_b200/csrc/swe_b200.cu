@@ -70,6 +70,27 @@ struct swe_ctx {
     int *p2p_flags = nullptr;                  // [npeers] sequence numbers written by the peers, [npeers] = error
     int p2p_seq = 0;
     std::vector<void *> p2p_imported;
+    // CUDA graphs of whole time steps (swe_run on launch-bound meshes): one instantiated graph per
+    // (scheme, flux, adaptive, dt, which state buffer is current); replayed instead of ~13 launches per step
+    struct StepGraph {
+        int scheme, fluxer, adaptive, parity, opts;
+        double dt;
+        cudaGraphExec_t exec;
+        int64_t launches;
+        bool cur_is_a_after;  // host-side state after the step
+    };
+    std::vector<StepGraph> graphs;
+    cudaStream_t gstream = nullptr;  // capture stream when the context runs on the legacy default stream
+    cudaEvent_t gev = nullptr;
+    int opt_graph = -1;              // -1 auto (meshes below kGraphAutoCells), 0 off, 1 on
+    // host-buffer pipeline (swe_submit_step_host): upload of batch n+1 and download of batch n-1 overlap the step of batch n
+    struct HostPipe {
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        double *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
+        cudaEvent_t in_ready[2], in_consumed[2], out_ready[2], out_free[2];
+        int64_t n = 0;
+        bool ok = false;
+    } pipe;
     // optional per-kernel CUDA-event timing (bench.py roofline): pairs recorded on c->stream
     bool ktiming = false;
     struct KtPair { cudaEvent_t a, b; int id; };
@@ -206,6 +227,18 @@ static void destroy_ctx(swe_ctx *c) {
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
     if (c->p2p_recv[1]) cudaFree(c->p2p_recv[1]);
     if (c->p2p_flags) cudaFree(c->p2p_flags);
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
+    if (c->gstream) cudaStreamDestroy(c->gstream);
+    if (c->gev) cudaEventDestroy(c->gev);
+    if (c->pipe.ok) {
+        cudaStreamSynchronize(c->pipe.s_in); cudaStreamSynchronize(c->pipe.s_out);
+        for (int q = 0; q < 2; ++q) {
+            cudaFree(c->pipe.in[q]); cudaFree(c->pipe.out[q]);
+            cudaEventDestroy(c->pipe.in_ready[q]); cudaEventDestroy(c->pipe.in_consumed[q]);
+            cudaEventDestroy(c->pipe.out_ready[q]); cudaEventDestroy(c->pipe.out_free[q]);
+        }
+        cudaStreamDestroy(c->pipe.s_in); cudaStreamDestroy(c->pipe.s_out);
+    }
     for (auto &p : c->kt_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto &p : c->kt_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete c;
@@ -591,6 +624,75 @@ SWE_API int swe_get_state(swe_ctx *c, double *prim) {
     return swe_synchronize(c);
 }
 
+static int one_step_fwd(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt);
+// ---- host-buffer pipeline: a stream of independent states, one time step each ----
+// Every submitted batch is uploaded from its (pinned) host buffer, stepped once, and downloaded into its (pinned)
+// output buffer. Three streams and double-buffered staging: the H2D copy of batch n+1 and the D2H copy of batch n-1
+// run while batch n is being stepped, so the steady-state cost per batch is max(H2D, step, D2H) instead of their sum
+// (PCIe is full duplex). Nothing blocks the host until swe_wait_host.
+static int pipe_init(swe_ctx *c) {
+    if (c->pipe.ok) return SWE_OK;
+    auto &p = c->pipe;
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+        CUDA_TRY(c, dalloc(&p.in[q], (size_t)3 * c->nt));
+        CUDA_TRY(c, dalloc(&p.out[q], (size_t)3 * c->nt));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&p.in_ready[q], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&p.in_consumed[q], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&p.out_ready[q], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&p.out_free[q], cudaEventDisableTiming));
+    }
+    p.n = 0; p.ok = true;
+    return SWE_OK;
+}
+// stage 1 of a batch: upload + conversion into the device state (compute stream ordered after it)
+static int pipe_begin(swe_ctx *c, const double *host_in) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = pipe_init(c);
+    if (rc) return rc;
+    auto &p = c->pipe;
+    const int b = (int)(p.n & 1);
+    if (p.n >= 2) CUDA_TRY(c, cudaStreamWaitEvent(p.s_in, p.in_consumed[b], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(p.in[b], host_in, sizeof(double) * 3 * c->nt, cudaMemcpyHostToDevice, p.s_in));
+    CUDA_TRY(c, cudaEventRecord(p.in_ready[b], p.s_in));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, p.in_ready[b], 0));
+    k_state_in<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, p.in[b], c->cur[0], c->cur[1], c->cur[2]);
+    if ((rc = launch_check(c, "k_state_in"))) return rc;
+    CUDA_TRY(c, cudaEventRecord(p.in_consumed[b], c->stream));
+    return SWE_OK;
+}
+// stage 3 of a batch: conversion + download
+static int pipe_end(swe_ctx *c, double *host_out) {
+    auto &p = c->pipe;
+    const int b = (int)(p.n & 1);
+    int rc;
+    if (p.n >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, p.out_free[b], 0));
+    k_state_out<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, c->cur[0], c->cur[1], c->cur[2], p.out[b]);
+    if ((rc = launch_check(c, "k_state_out"))) return rc;
+    CUDA_TRY(c, cudaEventRecord(p.out_ready[b], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(p.s_out, p.out_ready[b], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(host_out, p.out[b], sizeof(double) * 3 * c->nt, cudaMemcpyDeviceToHost, p.s_out));
+    CUDA_TRY(c, cudaEventRecord(p.out_free[b], p.s_out));
+    ++p.n;
+    return SWE_OK;
+}
+SWE_API int swe_submit_step_host(swe_ctx *c, const double *host_in, double *host_out, swe_scheme scheme, swe_flux flux,
+                                 swe_wavespeed ws, double dt) {
+    if (!c || !host_in || !host_out) return SWE_ERR_INVALID;
+    if (scheme < SWE_EULER || scheme > SWE_SSPRK3 || !(dt > 0.)) { c->err = "swe_submit_step_host: bad scheme / dt"; return SWE_ERR_INVALID; }
+    int rc;
+    if ((rc = pipe_begin(c, host_in))) return rc;
+    if ((rc = one_step_fwd(c, scheme, flux, ws, dt))) return rc;
+    return pipe_end(c, host_out);
+}
+SWE_API int swe_wait_host(swe_ctx *c) {
+    if (!c) return SWE_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->pipe.ok) { CUDA_TRY(c, cudaStreamSynchronize(c->pipe.s_in)); CUDA_TRY(c, cudaStreamSynchronize(c->pipe.s_out)); }
+    return swe_synchronize(c);
+}
+
 // ---- the stage pieces ----
 SWE_API int swe_enable_taps(swe_ctx *c, int on) {
     if (!c) return SWE_ERR_INVALID;
@@ -631,8 +733,9 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "pw2")) { if (value < 0 || value > 1) return bad("0 repaired, 1 as written"); c->opt_pw2 = value; }
     else if (!std::strcmp(key, "roe_fix")) { if (value < 0 || value > 1) return bad("0 as written (cl*ur), 1 cr*ur"); c->opt_roe_fix = value; }
     else if (!std::strcmp(key, "cfl_abs")) { if (value < 0 || value > 1) return bad("0 as written (signed max), 1 magnitudes"); c->opt_cfl_abs = value; }
+    else if (!std::strcmp(key, "graph")) { if (value < -1 || value > 1) return bad("-1 auto, 0 off, 1 on"); c->opt_graph = value; }
     else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > SWE_K1_TILED) return bad("0 gather kernel, 1 shared-memory staged tiles"); c->opt_tiled = value; }
-    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled)");
+    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, graph)");
     return SWE_OK;
 }
 SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
@@ -642,6 +745,7 @@ SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
     else if (!std::strcmp(key, "roe_fix")) *value = c->opt_roe_fix;
     else if (!std::strcmp(key, "cfl_abs")) *value = c->opt_cfl_abs;
     else if (!std::strcmp(key, "k1_tiled")) *value = c->opt_tiled;
+    else if (!std::strcmp(key, "graph")) *value = c->opt_graph;
     else { c->err = std::string("swe_get_option: unknown option ") + key; return SWE_ERR_INVALID; }
     return SWE_OK;
 }
@@ -832,6 +936,8 @@ SWE_API int swe_advance_dt(swe_ctx *c, int adaptive, double dt_fixed) {
 }
 
 static int read_scalar_fwd(swe_ctx *c, int idx, double *v);
+static int one_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt, bool dev_dt);
+static int one_step_fwd(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt) { return one_step(c, scheme, flux, ws, dt, false); }
 static int one_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, double dt, bool dev_dt) {
     int rc;
     auto upd = [&](double a0, double a1, double coef) {
@@ -861,6 +967,70 @@ SWE_API int swe_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed
     return swe_advance_dt(c, 0, dt);
 }
 
+// Launch-bound meshes (configs[0]-[1]: tens of microseconds of kernel time per step against ~13 launches): one
+// whole time step is captured into a CUDA graph and replayed. The two state buffers swap roles from step to step
+// (the first stage writes the other buffer so that U0 stays intact), hence one graph per parity.
+constexpr int kGraphAutoCells = 4 * 1024 * 1024;
+static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, int64_t nsteps, double dt, bool adaptive) {
+    int rc;
+    cudaStream_t user = c->stream;
+    if (user == 0) {  // the legacy default stream cannot be captured: run on an own stream, ordered after / before it
+        if (!c->gstream) {
+            CUDA_TRY(c, cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->gev, cudaEventDisableTiming));
+        }
+        CUDA_TRY(c, cudaEventRecord(c->gev, 0));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->gstream, c->gev, 0));
+        c->stream = c->gstream;
+    }
+    auto finish = [&](int code) {
+        if (user == 0) {
+            cudaEventRecord(c->gev, c->gstream);
+            cudaStreamWaitEvent(0, c->gev, 0);
+            c->stream = user;
+        }
+        return code;
+    };
+    const int fluxer = c->fluxer >= 0 ? c->fluxer : 3 * (int)flux + (int)ws;
+    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 5) | ((c->taps ? 1 : 0) << 6);
+    for (int64_t s = 0; s < nsteps; ++s) {
+        const int parity = (c->cur == c->bufA) ? 0 : 1;
+        swe_ctx::StepGraph *g = nullptr;
+        for (auto &q : c->graphs)
+            if (q.scheme == (int)scheme && q.fluxer == fluxer && q.adaptive == (int)adaptive && q.parity == parity && q.opts == opts &&
+                (adaptive || q.dt == dt)) { g = &q; break; }
+        if (!g) {
+            if (c->graphs.size() >= 16) {  // many different fixed dt values: stop caching, plain launches
+                if ((rc = one_step(c, scheme, flux, ws, dt, adaptive))) return finish(rc);
+                if ((rc = swe_advance_dt(c, adaptive ? 1 : 0, dt))) return finish(rc);
+                continue;
+            }
+            const int64_t l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            rc = one_step(c, scheme, flux, ws, dt, adaptive);
+            if (!rc) rc = swe_advance_dt(c, adaptive ? 1 : 0, dt);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return finish(rc); }
+            if (e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return finish(SWE_ERR_CUDA); }
+            swe_ctx::StepGraph ng{(int)scheme, fluxer, (int)adaptive, parity, opts, dt, nullptr, c->launches - l0, c->cur == c->bufA};
+            e = cudaGraphInstantiate(&ng.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return finish(SWE_ERR_CUDA); }
+            c->graphs.push_back(ng);
+            g = &c->graphs.back();
+            c->launches = l0;  // counted when the graph is launched
+        }
+        CUDA_TRY(c, cudaGraphLaunch(g->exec, c->stream));
+        c->launches += g->launches;
+        // host-side bookkeeping of what the step did to the buffers
+        c->cur = g->cur_is_a_after ? c->bufA : c->bufB;
+        c->sav = (scheme == SWE_EULER) ? c->sav : (parity == 0 ? c->bufA : c->bufB);
+        c->saved_pending = false;
+    }
+    return finish(SWE_OK);
+}
+
 SWE_API int swe_run(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed ws, int64_t nsteps, double dt, double dt0) {
     if (!c) return SWE_ERR_INVALID;
     if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { c->err = "swe_run: unknown scheme"; return SWE_ERR_INVALID; }
@@ -874,6 +1044,8 @@ SWE_API int swe_run(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed 
         if ((rc = read_scalar_fwd(c, 1, &cur))) return rc;
         if (!(cur > 0.)) { c->err = "swe_run: adaptive mode needs dt0 > 0 (no dt stored on the device yet)"; return SWE_ERR_INVALID; }
     }
+    const bool use_graph = (c->opt_graph == 1 || (c->opt_graph < 0 && c->nt <= kGraphAutoCells)) && !c->ktiming && nsteps >= 4;
+    if (use_graph) return run_graphed(c, scheme, flux, ws, nsteps, dt, adaptive);
     for (int64_t s = 0; s < nsteps; ++s) {
         if ((rc = one_step(c, scheme, flux, ws, dt, adaptive))) return rc;
         if ((rc = swe_advance_dt(c, adaptive ? 1 : 0, dt))) return rc;

@@ -404,6 +404,27 @@ SWE_API int swe_dist_group_run(swe_dist **ranks, int32_t world, swe_scheme schem
     return rc;
 }
 
+// host-buffer pipeline on a rank (see swe_submit_step_host): local state (owned + halo cells) in, one step, local state out
+SWE_API int swe_dist_submit_step_host(swe_dist *d, const double *host_in, double *host_out, swe_scheme scheme, swe_flux flux,
+                                      swe_wavespeed ws, double dt) {
+    if (!d || !host_in || !host_out) return SWE_ERR_INVALID;
+    if (scheme < SWE_EULER || scheme > SWE_SSPRK3 || !(dt > 0.)) { d->err = "swe_dist_submit_step_host: bad scheme / dt"; return SWE_ERR_INVALID; }
+    DIST_CTX(d, pipe_begin(d->ctx, host_in));
+    d->pending = false;  // the uploaded local state carries its own halo cells
+    int rc = dist_one_step(d, scheme, flux, ws, dt, false);
+    if (rc) return rc;
+    if ((rc = dist_pull(d))) return rc;  // halo cells of the result before it is downloaded
+    DIST_CTX(d, pipe_end(d->ctx, host_out));
+    return SWE_OK;
+}
+SWE_API int swe_dist_wait_host(swe_dist *d) {
+    if (!d) return SWE_ERR_INVALID;
+    swe_ctx *c = d->ctx;
+    DIST_TRY(d, cudaSetDevice(c->device));
+    if (c->pipe.ok) { DIST_TRY(d, cudaStreamSynchronize(c->pipe.s_in)); DIST_TRY(d, cudaStreamSynchronize(c->pipe.s_out)); }
+    return swe_dist_synchronize(d);
+}
+
 SWE_API int swe_dist_synchronize(swe_dist *d) {
     if (!d) return SWE_ERR_INVALID;
     swe_ctx *c = d->ctx;

@@ -155,6 +155,15 @@ class DistSolver(_DistBase):
     def synchronize(self):
         self._check(capi.lib().swe_dist_synchronize(self._d), self._d)
 
+    def submit_step_host(self, in_ptr: int, out_ptr: int, scheme, dt: float):
+        sc = capi.SCHEMES[scheme.lower()] if isinstance(scheme, str) else int(scheme)
+        self._check(capi.lib().swe_dist_submit_step_host(
+            self._d, C.cast(C.c_void_p(in_ptr), C.POINTER(C.c_double)), C.cast(C.c_void_p(out_ptr), C.POINTER(C.c_double)),
+            sc, self.sd.flux, self.sd.wavespeed, float(dt)), self._d)
+
+    def wait_host(self):
+        self._check(capi.lib().swe_dist_wait_host(self._d), self._d)
+
     def cfl_dt(self) -> float:
         v = C.c_double()
         self._check(capi.lib().swe_dist_cfl_dt(self._d, C.byref(v)), self._d)

@@ -93,6 +93,15 @@ class SpaceDisc:
     def get_state_async(self, pinned_ptr: int):
         self._call("swe_get_state_async", C.cast(C.c_void_p(pinned_ptr), C.POINTER(C.c_double)))
 
+    def submit_step_host(self, in_ptr: int, out_ptr: int, scheme, dt: float):
+        """Host-buffer pipeline (swe_submit_step_host): upload in_ptr -> one step -> download into out_ptr, asynchronous."""
+        sc = capi.SCHEMES[scheme.lower()] if isinstance(scheme, str) else int(scheme)
+        self._call("swe_submit_step_host", C.cast(C.c_void_p(in_ptr), C.POINTER(C.c_double)),
+                   C.cast(C.c_void_p(out_ptr), C.POINTER(C.c_double)), sc, self.flux, self.wavespeed, float(dt))
+
+    def wait_host(self):
+        self._call("swe_wait_host")
+
     def ComputeInterfaceValues(self):
         self._call("swe_compute_interface_values")
 
