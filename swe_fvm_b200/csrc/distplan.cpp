@@ -33,6 +33,7 @@ static void finish_plan(swe_dist_plan &p) {
     for (auto &pe : p.peers)
         for (int64_t c : pe.send) sent[(size_t)c] = 1;
     p.cls.assign((size_t)m.nt, 0);
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t t = 0; t < m.nt; ++t) {
         if (!p.owned[(size_t)t]) { p.cls[(size_t)t] = 3; continue; }
         bool dep = false;
@@ -44,6 +45,7 @@ static void finish_plan(swe_dist_plan &p) {
     }
     // CFL candidates are valid (and needed) only on edges that touch an owned cell
     p.cfl_mask.assign((size_t)m.ne, 0);
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t e = 0; e < m.ne; ++e) {
         const int64_t a = m.et[2 * e], b = m.et[2 * e + 1];
         p.cfl_mask[(size_t)e] = (p.owned[(size_t)a] || (b >= 0 && p.owned[(size_t)b])) ? 1 : 0;

@@ -19,12 +19,28 @@
 #include <fstream>
 #include <numeric>
 #include <sstream>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <unordered_map>
 
 namespace swe {
 
 static thread_local std::string g_host_error;
+
+// Launchers such as torchrun export OMP_NUM_THREADS=1, which would make the one-off set-up of a 64M-cell rank take
+// half a minute; SWE_HOST_THREADS overrides, otherwise the cores are shared among the ranks of this node.
+int host_threads() {
+    static int n = 0;
+    if (n) return n;
+    if (const char *e = std::getenv("SWE_HOST_THREADS")) { n = std::max(1, std::atoi(e)); return n; }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw <= 0) hw = 8;
+    int lw = 1;
+    if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) lw = std::max(1, std::atoi(e));
+    n = std::max(1, std::min(32, hw / lw));
+    return n;
+}
 void set_host_error(const std::string &s) { g_host_error = s; }
 const char *host_error() { return g_host_error.c_str(); }
 
@@ -115,78 +131,66 @@ void build_struct(swe_hostmesh &m, int64_t ni, int64_t nj, double h, int64_t i0,
     m.nn = nv + ni * nj;
     m.nt = 4 * ni * nj;
     m.ne = 6 * ni * nj + ni + nj;
-    m.geom.assign((size_t)m.nn * 3, 0.0);
+    m.geom.resize((size_t)m.nn * 3);
+    m.tp.resize((size_t)m.nt * 3); m.te.resize((size_t)m.nt * 3); m.tt.resize((size_t)m.nt * 3);
+    m.ep.resize((size_t)m.ne * 2); m.et.resize((size_t)m.ne * 2);
+    // Edge ids in closed form (the running counter m_curr_e of upstream's generator, resolved): a square visits its
+    // edges in the order [bottom if j == 0], B-R diagonal, B-L diagonal, right, R-T diagonal, top, T-L diagonal,
+    // [left if i == 0]; row 0 creates 7 edges per square (+1 for i == 0), the other rows 6 (+1).
+    auto row_base = [&](int64_t j) { return j == 0 ? (int64_t)0 : (7 * ni + 1) + (j - 1) * (6 * ni + 1); };
+    auto first = [&](int64_t j, int64_t i) { return row_base(j) + i * (j == 0 ? 7 : 6) + (i > 0 ? 1 : 0) + (j == 0 ? 1 : 0); };  // id of the B-R diagonal
+    auto e_top = [&](int64_t j, int64_t i) { return first(j, i) + 4; };
+    auto e_right = [&](int64_t j, int64_t i) { return first(j, i) + 2; };
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t j = 0; j <= nj; ++j)
         for (int64_t i = 0; i <= ni; ++i) {
-            int64_t p = j * (ni + 1) + i;
-            m.geom[3 * p + 0] = double(i0 + i) * h;
-            m.geom[3 * p + 1] = double(j0 + j) * h;
+            double *g = &m.geom[3 * (j * (ni + 1) + i)];
+            g[0] = double(i0 + i) * h; g[1] = double(j0 + j) * h; g[2] = 0.;
         }
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t j = 0; j < nj; ++j)
-        for (int64_t i = 0; i < ni; ++i) {
-            int64_t p = nv + j * ni + i;
-            m.geom[3 * p + 0] = (double(i0 + i) + 0.5) * h;
-            m.geom[3 * p + 1] = (double(j0 + j) + 0.5) * h;
-        }
-    m.tp.assign((size_t)m.nt * 3, -1);
-    m.te.assign((size_t)m.nt * 3, -1);
-    m.tt.assign((size_t)m.nt * 3, -1);
-    m.ep.assign((size_t)m.ne * 2, -1);
-    m.et.assign((size_t)m.ne * 2, -1);
-    std::vector<int64_t> top_edge((size_t)ni, -1);  // top edge ids of the previous row
-    int64_t cur = 0;
-    auto new_edge = [&](int64_t a, int64_t b, int64_t t) {
-        int64_t e = cur++;
-        m.ep[2 * e] = std::min(a, b); m.ep[2 * e + 1] = std::max(a, b);
-        m.et[2 * e] = t; m.et[2 * e + 1] = -1;
-        return e;
-    };
-    auto second_visit = [&](int64_t e, int64_t t) {
-        m.et[2 * e + 1] = m.et[2 * e];
-        m.et[2 * e] = t;
-    };
-    for (int64_t j = 0; j < nj; ++j) {
-        int64_t right_prev = -1;
         for (int64_t i = 0; i < ni; ++i) {
             const int64_t s = j * ni + i;
             const int64_t v00 = j * (ni + 1) + i, v10 = v00 + 1, v01 = v00 + (ni + 1), v11 = v01 + 1;
             const int64_t c = nv + s;
+            double *g = &m.geom[3 * c];
+            g[0] = (double(i0 + i) + 0.5) * h; g[1] = (double(j0 + j) + 0.5) * h; g[2] = 0.;
             const int64_t B = 4 * s, R = B + 1, T = B + 2, L = B + 3;
             int64_t *tp = &m.tp[3 * B];
             tp[0] = v00; tp[1] = v10; tp[2] = c;    // Bottom
             tp[3] = v10; tp[4] = v11; tp[5] = c;    // Right
             tp[6] = v11; tp[7] = v01; tp[8] = c;    // Top
             tp[9] = v01; tp[10] = v00; tp[11] = c;  // Left
-            int64_t e_bot;
-            if (j == 0) e_bot = new_edge(v00, v10, B);
-            else { e_bot = top_edge[i]; second_visit(e_bot, B); }
-            const int64_t e_b1 = new_edge(v10, c, B);  // B.k1, later R.k2
-            const int64_t e_b2 = new_edge(c, v00, B);  // B.k2, later L.k1
-            const int64_t e_right = new_edge(v10, v11, R);
-            second_visit(e_b1, R);
-            const int64_t e_r1 = new_edge(v11, c, R);  // R.k1, later T.k2
-            const int64_t e_top = new_edge(v11, v01, T);
-            second_visit(e_r1, T);
-            const int64_t e_t1 = new_edge(v01, c, T);  // T.k1, later L.k2
-            int64_t e_left;
-            if (i == 0) e_left = new_edge(v01, v00, L);
-            else { e_left = right_prev; second_visit(e_left, L); }
-            second_visit(e_b2, L);
-            second_visit(e_t1, L);
+            const int64_t f = first(j, i);
+            const int64_t e_b1 = f, e_b2 = f + 1, e_rt = f + 2, e_r1 = f + 3, e_tp = f + 4, e_t1 = f + 5;
+            const int64_t e_bot = j == 0 ? f - 1 : e_top(j - 1, i);
+            const int64_t e_left = i == 0 ? f + 6 : e_right(j, i - 1);
             int64_t *te = &m.te[3 * B];
-            te[0] = e_bot;   te[1] = e_b1; te[2] = e_b2;
-            te[3] = e_right; te[4] = e_r1; te[5] = e_b1;
-            te[6] = e_top;   te[7] = e_t1; te[8] = e_r1;
-            te[9] = e_left;  te[10] = e_b2; te[11] = e_t1;
+            te[0] = e_bot;  te[1] = e_b1; te[2] = e_b2;
+            te[3] = e_rt;   te[4] = e_r1; te[5] = e_b1;
+            te[6] = e_tp;   te[7] = e_t1; te[8] = e_r1;
+            te[9] = e_left; te[10] = e_b2; te[11] = e_t1;
+            const int64_t below = (j > 0) ? 4 * (s - ni) + 2 : -1, east = (i < ni - 1) ? 4 * (s + 1) + 3 : -1;
+            const int64_t above = (j < nj - 1) ? 4 * (s + ni) : -1, west = (i > 0) ? 4 * (s - 1) + 1 : -1;
             int64_t *tt = &m.tt[3 * B];
-            tt[0] = (j > 0) ? 4 * (s - ni) + 2 : -1;      tt[1] = R; tt[2] = L;
-            tt[3] = (i < ni - 1) ? 4 * (s + 1) + 3 : -1;  tt[4] = T; tt[5] = B;
-            tt[6] = (j < nj - 1) ? 4 * (s + ni) + 0 : -1; tt[7] = L; tt[8] = R;
-            tt[9] = (i > 0) ? 4 * (s - 1) + 1 : -1;       tt[10] = B; tt[11] = T;
-            top_edge[i] = e_top;
-            right_prev = e_right;
+            tt[0] = below; tt[1] = R; tt[2] = L;
+            tt[3] = east;  tt[4] = T; tt[5] = B;
+            tt[6] = above; tt[7] = L; tt[8] = R;
+            tt[9] = west;  tt[10] = B; tt[11] = T;
+            // every edge is written by the square that visits it first: sorted end points, (later, earlier) cells
+            auto edge = [&](int64_t e, int64_t a, int64_t b, int64_t later, int64_t earlier) {
+                m.ep[2 * e] = std::min(a, b); m.ep[2 * e + 1] = std::max(a, b);
+                m.et[2 * e] = later; m.et[2 * e + 1] = earlier;
+            };
+            if (j == 0) edge(e_bot, v00, v10, B, -1);
+            edge(e_b1, v10, c, R, B);
+            edge(e_b2, c, v00, L, B);
+            edge(e_rt, v10, v11, east >= 0 ? east : R, east >= 0 ? R : -1);
+            edge(e_r1, v11, c, T, R);
+            edge(e_tp, v11, v01, above >= 0 ? above : T, above >= 0 ? T : -1);
+            edge(e_t1, v01, c, L, T);
+            if (i == 0) edge(e_left, v01, v00, L, -1);
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -526,7 +530,7 @@ static void triang_average(const double *p0, const double *p1, const double *p2,
 void case_initial_state(const swe_case &c, const swe_hostmesh &m, int quad_n, double t, double *prim) {
     const double third = 1. / 3.;
     // the reference's IC loop carries `#pragma omp parallel for` too (examples/Main.cpp:210)
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t i = 0; i < m.nt; ++i) {
         const double *p0 = &m.geom[3 * m.tp[3 * i]], *p1 = &m.geom[3 * m.tp[3 * i + 1]], *p2 = &m.geom[3 * m.tp[3 * i + 2]];
         // VolumeDomainWrapper::At = Domain::T(i)[2] (src/ValueField.cpp:8-10, src/Bathymetry.cpp:24-27)
@@ -681,7 +685,7 @@ SWE_API int swe_case_eval(const swe_case *c, double x, double y, double t, doubl
 
 SWE_API int swe_case_set_bathymetry(const swe_case *c, swe_hostmesh *m) {
     if (!c || !m || c->kind < 0 || c->kind > SWE_CASE_BOWL_HUMP) { set_host_error("swe_case_set_bathymetry: bad argument"); return SWE_ERR_INVALID; }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(swe::host_threads())
     for (int64_t p = 0; p < m->nn; ++p) {
         double o[4];
         swe::case_eval(*c, m->geom[3 * p], m->geom[3 * p + 1], 0., o);

@@ -19,6 +19,7 @@ struct swe_hostmesh {
 };
 
 namespace swe {
+int host_threads();  // threads for the host-side set-up loops (SWE_HOST_THREADS, else cores / LOCAL_WORLD_SIZE, <= 32)
 void set_host_error(const std::string &s);
 const char *host_error();
 void build_topology(swe_hostmesh &m, const std::vector<int64_t> &bnd_pairs);

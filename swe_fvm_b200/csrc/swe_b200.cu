@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/swe_b200.h"
@@ -19,6 +21,7 @@
 #include "swe_cases.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 using namespace swe;
 
@@ -119,6 +122,8 @@ static inline void kt_end(swe_ctx *c, int h) {
 
 static thread_local std::string g_create_error;
 
+using swe::host_threads;
+
 #define CUDA_TRY(ctx, call)                                                                      \
     do {                                                                                         \
         cudaError_t e_ = (call);                                                                 \
@@ -182,7 +187,7 @@ static cudaError_t morton_order(const std::vector<double> &x, const std::vector<
                                 bool curve = true) {
     const size_t n = x.size();
     std::vector<uint64_t> keys(n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         uint64_t qx = (uint64_t)std::min(2097151.0, std::max(0.0, (x[i] - x0) * sx));
         uint64_t qy = (uint64_t)std::min(2097151.0, std::max(0.0, (y[i] - y0) * sy));
@@ -209,7 +214,7 @@ static cudaError_t morton_order(const std::vector<double> &x, const std::vector<
 #undef MO_TRY
     cleanup();
     newid.resize(n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (int64_t k = 0; k < (int64_t)n; ++k) newid[order[k]] = (int)k;
     return cudaSuccess;
 }
@@ -340,7 +345,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     // validate ids and boundary tags (only SOLID_WALL is implemented upstream, src/SpaceDisc.cpp:66-72)
     {
         int bad = 0;  // 1 edge_elements, 2 boundary tag, 3 edge_nodes, 4 element_nodes, 5 element_edges, 6 neighbours
-#pragma omp parallel for schedule(static) reduction(max : bad)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : bad)
         for (int64_t e = 0; e < ne; ++e) {
             const int64_t a = mesh->edge_elements[2 * e], b = mesh->edge_elements[2 * e + 1];
             if (a < 0 || a >= nt || b >= nt) bad = std::max(bad, 1);
@@ -352,7 +357,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
         if (bad == 1) return fail(SWE_ERR_INVALID, "swe_create: edge_elements id out of range");
         if (bad == 2) return fail(SWE_ERR_INVALID, "swe_create: only SOLID_WALL (-1) boundaries are supported");
         if (bad == 3) return fail(SWE_ERR_INVALID, "swe_create: edge_nodes id out of range");
-#pragma omp parallel for schedule(static) reduction(max : bad)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : bad)
         for (int64_t k = 0; k < 3 * nt; ++k) {
             if (mesh->element_nodes[k] < 0 || mesh->element_nodes[k] >= nn) bad = std::max(bad, 4);
             if (mesh->element_edges[k] < 0 || mesh->element_edges[k] >= ne) bad = std::max(bad, 5);
@@ -389,6 +394,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     try {
         if (c->reordered) {
             double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(min : x0, y0) reduction(max : x1, y1)
             for (int64_t p = 0; p < nn; ++p) {
                 x0 = std::min(x0, mesh->geometry[3 * p]); x1 = std::max(x1, mesh->geometry[3 * p]);
                 y0 = std::min(y0, mesh->geometry[3 * p + 1]); y1 = std::max(y1, mesh->geometry[3 * p + 1]);
@@ -396,6 +402,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
             const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
             const double sc = 2097152.0 / span;
             std::vector<double> xs((size_t)nt), ys((size_t)nt);
+#pragma omp parallel for schedule(static) num_threads(host_threads())
             for (int64_t t = 0; t < nt; ++t) {
                 const int64_t *q = &mesh->element_nodes[3 * t];
                 xs[t] = (mesh->geometry[3 * q[0]] + mesh->geometry[3 * q[1]] + mesh->geometry[3 * q[2]]) / 3.;
@@ -404,6 +411,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
             if ((ce = morton_order(xs, ys, x0, y0, sc, sc, cell_new, cell_class, reorder != 0)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
             if (reorder != 0) {
             xs.resize((size_t)ne); ys.resize((size_t)ne);
+#pragma omp parallel for schedule(static) num_threads(host_threads())
             for (int64_t e = 0; e < ne; ++e) {
                 const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
                 xs[e] = 0.5 * (mesh->geometry[3 * a] + mesh->geometry[3 * b]);
@@ -411,6 +419,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
             }
             if ((ce = morton_order(xs, ys, x0, y0, sc, sc, edge_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
             xs.resize((size_t)nn); ys.resize((size_t)nn);
+#pragma omp parallel for schedule(static) num_threads(host_threads())
             for (int64_t p = 0; p < nn; ++p) { xs[p] = mesh->geometry[3 * p]; ys[p] = mesh->geometry[3 * p + 1]; }
             if ((ce = morton_order(xs, ys, x0, y0, sc, sc, node_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
             } else {
@@ -445,7 +454,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     {
         std::vector<int> h_tp((size_t)3 * nt), h_tt((size_t)3 * nt), h_te((size_t)3 * nt);
         int inconsistent = 0;
-#pragma omp parallel for schedule(static) reduction(max : inconsistent)
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : inconsistent)
         for (int64_t t = 0; t < nt; ++t) {
             const int d = cell_new[t];
             for (int k = 0; k < 3; ++k) {
@@ -476,22 +485,32 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
         CREATE_TRY(cudaMemcpy(c->tp, h_tp.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(c->tt, h_tt.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(c->te, h_te.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
-        // node -> incident cells (CSR, device numbering): pass 2 gathers the node maxima over it
-        std::vector<int> start((size_t)nn + 1, 0);
-        for (int64_t k = 0; k < 3 * nt; ++k) start[(size_t)h_tp[k] + 1]++;
-        for (int64_t p = 0; p < nn; ++p) start[p + 1] += start[p];
-        std::vector<int> fill(start.begin(), start.end() - 1), cells((size_t)3 * nt);
-        for (int64_t d = 0; d < nt; ++d)
-            for (int k = 0; k < 3; ++k) cells[fill[h_tp[(size_t)k * nt + d]]++] = (int)d;
-        CREATE_TRY(dalloc(&c->n2c_start, (size_t)nn + 1)); CREATE_TRY(dalloc(&c->n2c_cells, (size_t)3 * nt));
-        CREATE_TRY(cudaMemcpy(c->n2c_start, start.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(c->n2c_cells, cells.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
+        // node -> incident cells (CSR, device numbering; pass 2 gathers the node maxima over it), built on the device:
+        // histogram of the node ids -> exclusive scan = row starts; stable sort of (node, cell) pairs = row contents
+        {
+            int *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr;
+            void *tmp = nullptr;
+            size_t tb1 = 0, tb2 = 0;
+            CREATE_TRY(dalloc(&c->n2c_start, (size_t)nn + 1)); CREATE_TRY(dalloc(&c->n2c_cells, (size_t)3 * nt));
+            CREATE_TRY(dalloc(&keys_out, (size_t)3 * nt)); CREATE_TRY(dalloc(&vals_in, (size_t)3 * nt));
+            keys_in = c->tp;  // tp[k * nt + d] = node of local corner k of cell d
+            CREATE_TRY(cudaMemset(c->n2c_start, 0, sizeof(int) * (nn + 1)));
+            k_n2c_count<<<nblk(3 * nt, 256), 256>>>((int)(3 * nt), (int)nt, keys_in, c->n2c_start + 1, vals_in);
+            CREATE_TRY(cudaGetLastError());
+            CREATE_TRY(cub::DeviceScan::InclusiveSum(nullptr, tb1, c->n2c_start + 1, c->n2c_start + 1, (int)nn));
+            CREATE_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb2, keys_in, keys_out, vals_in, c->n2c_cells, (int64_t)(3 * nt)));
+            CREATE_TRY(cudaMalloc(&tmp, std::max(tb1, tb2)));
+            CREATE_TRY(cub::DeviceScan::InclusiveSum(tmp, tb1, c->n2c_start + 1, c->n2c_start + 1, (int)nn));
+            CREATE_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb2, keys_in, keys_out, vals_in, c->n2c_cells, (int64_t)(3 * nt)));
+            CREATE_TRY(cudaDeviceSynchronize());
+            cudaFree(tmp); cudaFree(keys_out); cudaFree(vals_in);
+        }
     }
     int *d_ep0 = nullptr, *d_ep1 = nullptr, *d_et0 = nullptr, *d_et1 = nullptr;
     {
         std::vector<int> h((size_t)4 * ne);
         int *ep0 = h.data(), *ep1 = ep0 + ne, *et0 = ep1 + ne, *et1 = et0 + ne;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
         for (int64_t e = 0; e < ne; ++e) {
             const int d = edge_new[e];
             ep0[d] = node_new[mesh->edge_nodes[2 * e]]; ep1[d] = node_new[mesh->edge_nodes[2 * e + 1]];
@@ -505,7 +524,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     }
     {
         std::vector<double> h((size_t)4 * nn);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
         for (int64_t p = 0; p < nn; ++p) {
             double *q = &h[(size_t)4 * node_new[p]];
             q[0] = mesh->geometry[3 * p]; q[1] = mesh->geometry[3 * p + 1]; q[2] = mesh->geometry[3 * p + 2]; q[3] = 0.;
@@ -515,12 +534,15 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     }
     if (c->reordered) {
         std::vector<int> inv((size_t)std::max(std::max(nt, ne), nn));
+#pragma omp parallel for schedule(static) num_threads(host_threads())
         for (int64_t t = 0; t < nt; ++t) inv[cell_new[t]] = (int)t;
         CREATE_TRY(dalloc(&c->cell_old, (size_t)nt));
         CREATE_TRY(cudaMemcpy(c->cell_old, inv.data(), sizeof(int) * nt, cudaMemcpyHostToDevice));
+#pragma omp parallel for schedule(static) num_threads(host_threads())
         for (int64_t e = 0; e < ne; ++e) inv[edge_new[e]] = (int)e;
         CREATE_TRY(dalloc(&c->edge_old, (size_t)ne));
         CREATE_TRY(cudaMemcpy(c->edge_old, inv.data(), sizeof(int) * ne, cudaMemcpyHostToDevice));
+#pragma omp parallel for schedule(static) num_threads(host_threads())
         for (int64_t p = 0; p < nn; ++p) inv[node_new[p]] = (int)p;
         CREATE_TRY(dalloc(&c->node_old, (size_t)nn));
         CREATE_TRY(cudaMemcpy(c->node_old, inv.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
@@ -559,7 +581,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(cudaMemset(c->f2, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->dti, 0, sizeof(double) * nt)); CREATE_TRY(cudaMemset(c->cls, 0, nt));
     CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 8));
-    const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 0, 0, 0, 0};
+    const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0};  // [0] min_len, [1] dt, [2] time, [3] running min, [4] global min_len
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
@@ -931,7 +953,7 @@ SWE_API int swe_set_dt(swe_ctx *c, double dt) {
 SWE_API int swe_advance_dt(swe_ctx *c, int adaptive, double dt_fixed) {
     if (!c) return SWE_ERR_INVALID;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    k_post_step<<<1, 1, 0, c->stream>>>(dev_fields(c), dt_fixed, adaptive);
+    k_post_step<<<1, 1, 0, c->stream>>>(dev_fields(c), dt_fixed, adaptive, 0);
     return launch_check(c, "k_post_step");
 }
 

@@ -49,6 +49,11 @@ struct swe_dist {
     std::vector<void *> imported;
     int seq = 0, minseq = 0;
     bool pending = false;            // an exchange was pushed and not yet pulled
+    // the global CFL minimum of the last step was pushed but not yet pulled: it is first NEEDED by the stage update of
+    // the next step, so the pull (a wait for the slowest rank) is deferred behind that step's first K1 + K2
+    bool min_pending = false;
+    int min_adaptive = 0;
+    double min_dt_fixed = 0.;
     cudaStream_t own_stream = nullptr;  // group mode: every rank of the process gets its own non-blocking stream
     long long timeout_cycles = 0;
     DistHello hello{};
@@ -222,6 +227,24 @@ static int dist_pull(swe_dist *d) {  // wait for every peer's flag, unpack into 
     return rc;
 }
 
+// pull the global minimum of the previous step and advance time / dt with it
+static int dist_finish_min(swe_dist *d, bool also_scal0) {
+    swe_ctx *c = d->ctx;
+    if (!d->min_pending) return SWE_OK;
+    d->min_pending = false;
+    int rc;
+    if (d->plan->world > 1) {
+        const int kt = kt_begin(c, KT_MIN);
+        k_min_pull<<<1, 32, 0, c->stream>>>(c->scal, d->min_table(), d->min_flags(), d->plan->world, d->minseq, d->timeout_cycles,
+                                            c->flags + 5, also_scal0 ? 1 : 0);
+        kt_end(c, kt);
+        if ((rc = launch_check(c, "k_min_pull"))) { d->err = c->err; return rc; }
+    }
+    k_post_step<<<1, 1, 0, c->stream>>>(dev_fields(c), d->min_dt_fixed, d->min_adaptive, d->plan->world > 1 ? 4 : 0);
+    if ((rc = launch_check(c, "k_post_step"))) { d->err = c->err; return rc; }
+    return SWE_OK;
+}
+
 static int dist_interface_values(swe_dist *d) {
     swe_ctx *c = d->ctx;
     if (!d->pending) DIST_CTX(d, interface_values_range(c, 0, c->nt, true, true));
@@ -241,6 +264,9 @@ static int dist_stage(swe_dist *d, swe_flux flux, swe_wavespeed ws, double a0, d
     int rc;
     if ((rc = dist_interface_values(d))) return rc;
     DIST_CTX(d, swe_compute_fluxes(c, flux, ws));
+    // dt of THIS step from the previous step's global minimum: first needed by the stage update below, so the wait
+    // for the slowest rank hides behind the reconstruction + flux kernels above (must precede this step's push)
+    if ((rc = dist_finish_min(d, false))) return rc;
     if (last && world > 1) {  // this rank's CFL minimum to every rank's table (needed only by the next step's dt)
         const int seq = ++d->minseq;
         const int kt = kt_begin(c, KT_MIN);
@@ -275,19 +301,11 @@ static int dist_one_step(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wave
                                  {{0., 1., 1.}, {0.5, 0.5, 0.5}, {0, 0, 0}},
                                  {{0., 1., 1.}, {0.75, 0.25, 0.25}, {1. / 3., 2. / 3., 2. / 3.}}};
     const int ns = scheme == SWE_EULER ? 1 : scheme == SWE_SSPRK2 ? 2 : 3;
-    swe_ctx *c = d->ctx;
     int rc;
     for (int k = 0; k < ns; ++k) {
         const St &s = tab[scheme][k];
         if ((rc = dist_stage(d, flux, ws, s.a0, s.a1, dev_dt ? 0. : s.coef * dt, dev_dt ? s.coef : 0., k == 0 && ns > 1, k == ns - 1)))
             return rc;
-    }
-    if (d->plan->world > 1) {
-        const int kt = kt_begin(c, KT_MIN);
-        k_min_pull<<<1, 32, 0, c->stream>>>(c->scal, d->min_table(), d->min_flags(), d->plan->world, d->minseq, d->timeout_cycles,
-                                            c->flags + 5);
-        kt_end(c, kt);
-        if ((rc = launch_check(c, "k_min_pull"))) { d->err = c->err; return rc; }
     }
     return SWE_OK;
 }
@@ -366,7 +384,8 @@ SWE_API int swe_dist_step(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wav
     DIST_TRY(d, cudaSetDevice(d->ctx->device));
     int rc = dist_one_step(d, scheme, flux, ws, dt, false);
     if (rc) return rc;
-    DIST_CTX(d, swe_advance_dt(d->ctx, 0, dt));
+    d->min_pending = true; d->min_adaptive = 0; d->min_dt_fixed = dt;
+    if (d->plan->world == 1) return dist_finish_min(d, false);  // nothing to wait for on one GPU
     return SWE_OK;
 }
 
@@ -374,6 +393,8 @@ static int dist_run_begin(swe_dist *d, swe_scheme scheme, double dt, double dt0)
     if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { d->err = "swe_dist_run: unknown scheme"; return SWE_ERR_INVALID; }
     if (!(dt > 0.) && !(dt0 > 0.)) { d->err = "swe_dist_run: adaptive mode needs dt0 > 0"; return SWE_ERR_INVALID; }
     DIST_TRY(d, cudaSetDevice(d->ctx->device));
+    int rc = dist_finish_min(d, true);
+    if (rc) return rc;
     if (!(dt > 0.)) DIST_CTX(d, swe_set_dt(d->ctx, dt0));
     return SWE_OK;
 }
@@ -382,7 +403,8 @@ static int dist_run_one(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_waves
     DIST_TRY(d, cudaSetDevice(d->ctx->device));
     int rc = dist_one_step(d, scheme, flux, ws, dt, adaptive);
     if (rc) return rc;
-    DIST_CTX(d, swe_advance_dt(d->ctx, adaptive ? 1 : 0, dt));
+    d->min_pending = true; d->min_adaptive = adaptive ? 1 : 0; d->min_dt_fixed = dt;
+    if (d->plan->world == 1) return dist_finish_min(d, false);
     return SWE_OK;
 }
 
@@ -409,10 +431,13 @@ SWE_API int swe_dist_submit_step_host(swe_dist *d, const double *host_in, double
                                       swe_wavespeed ws, double dt) {
     if (!d || !host_in || !host_out) return SWE_ERR_INVALID;
     if (scheme < SWE_EULER || scheme > SWE_SSPRK3 || !(dt > 0.)) { d->err = "swe_dist_submit_step_host: bad scheme / dt"; return SWE_ERR_INVALID; }
+    { int rc0 = dist_finish_min(d, false); if (rc0) return rc0; }
     DIST_CTX(d, pipe_begin(d->ctx, host_in));
     d->pending = false;  // the uploaded local state carries its own halo cells
     int rc = dist_one_step(d, scheme, flux, ws, dt, false);
     if (rc) return rc;
+    d->min_pending = true; d->min_adaptive = 0; d->min_dt_fixed = dt;
+    if (d->plan->world == 1 && (rc = dist_finish_min(d, false))) return rc;
     if ((rc = dist_pull(d))) return rc;  // halo cells of the result before it is downloaded
     DIST_CTX(d, pipe_end(d->ctx, host_out));
     return SWE_OK;
@@ -431,6 +456,7 @@ SWE_API int swe_dist_synchronize(swe_dist *d) {
     DIST_TRY(d, cudaSetDevice(c->device));
     int rc;
     if (d->pending && (rc = dist_pull(d))) return rc;  // order the stream after the exchange in flight
+    if ((rc = dist_finish_min(d, true))) return rc;    // ... and after the deferred global minimum
     DIST_TRY(d, cudaStreamSynchronize(c->stream));
     int flags[8];
     DIST_TRY(d, cudaMemcpy(flags, c->flags, sizeof(flags), cudaMemcpyDeviceToHost));
@@ -441,7 +467,13 @@ SWE_API int swe_dist_synchronize(swe_dist *d) {
 
 SWE_API int swe_dist_cfl_dt(swe_dist *d, double *dt) {
     if (!d || !dt) return SWE_ERR_INVALID;
-    DIST_CTX(d, swe_cfl_dt(d->ctx, dt));
+    DIST_TRY(d, cudaSetDevice(d->ctx->device));
+    int rc = dist_finish_min(d, true);
+    if (rc) return rc;
+    double v = 0.;  // scal[4] = global minimum on several GPUs, scal[0] on one
+    DIST_TRY(d, cudaMemcpyAsync(&v, d->ctx->scal + (d->plan->world > 1 ? 4 : 0), sizeof(double), cudaMemcpyDeviceToHost, d->ctx->stream));
+    DIST_TRY(d, cudaStreamSynchronize(d->ctx->stream));
+    *dt = 0.15 * v;
     return SWE_OK;
 }
 

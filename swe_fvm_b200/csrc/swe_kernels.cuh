@@ -829,10 +829,12 @@ __global__ void k_classify(DevMesh m, const double *w, signed char *cls) {
 }
 
 // after a step: time += dt_used; in adaptive mode dt = 0.15 * min_len (include/TimeDisc.h:13,22)
-__global__ void k_post_step(DevFields s, double dt_host, int adaptive) {
+// min_slot: where min_len_to_wavespeed of the finished step lives (0 on one GPU; 4 = the global minimum pulled from
+// the peer-memory table on several GPUs)
+__global__ void k_post_step(DevFields s, double dt_host, int adaptive, int min_slot) {
     const double used = adaptive ? s.scal[1] : dt_host;
     s.scal[2] += used;
-    if (adaptive) s.scal[1] = 0.15 * s.scal[0];
+    if (adaptive) s.scal[1] = 0.15 * s.scal[min_slot];
 }
 __global__ void k_set_scalar(double *p, double v) { *p = v; }
 
@@ -854,6 +856,14 @@ __global__ void k_setup_cells(int nt, const int *tp, const int *tt, const double
     cb[i] = g.z;
     const double ax = P1.x - P0.x, ay = P1.y - P0.y, bx = P2.x - P0.x, by = P2.y - P0.y;
     area[i] = 0.5 * fabs(ax * by - bx * ay);  // Domain::Area (:87-90)
+}
+
+// node -> cells CSR set-up: count the incident cells of every node and emit the cell id of each (corner, cell) pair
+__global__ void k_n2c_count(int n3, int nt, const int *tp, int *count, int *cell_of_pair) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n3) return;
+    atomicAdd(&count[tp[q]], 1);
+    cell_of_pair[q] = q % nt;
 }
 
 __global__ void k_setup_slots(int nt, const int *te, int *slotL, int *slotR) {
@@ -1045,7 +1055,11 @@ __global__ void k_min_push(const double *scal, MinPeers t, int world, int rank, 
     *(volatile int *)(t.flag[p] + rank) = seq;
     __threadfence_system();
 }
-__global__ void k_min_pull(double *scal, const double *buf, volatile int *flag, int world, int seq, long long timeout_cycles, int *err) {
+// The global minimum goes to scal[4]; scal[0] keeps belonging to the flux kernel (the pull is deferred into the
+// NEXT step, after its first flux evaluation has already overwritten scal[0]). also_scal0: a host query forces
+// the pull at the end of a step and wants the classic slot updated as well.
+__global__ void k_min_pull(double *scal, const double *buf, volatile int *flag, int world, int seq, long long timeout_cycles, int *err,
+                           int also_scal0) {
     const int p = threadIdx.x;
     if (p < world) {
         const long long t0 = clock64();
@@ -1059,7 +1073,8 @@ __global__ void k_min_pull(double *scal, const double *buf, volatile int *flag, 
     if (threadIdx.x == 0) {
         double mn = __ldcg(buf + (seq & 1) * kMaxRanks);
         for (int q = 1; q < world; ++q) { const double x = __ldcg(buf + (seq & 1) * kMaxRanks + q); mn = (x < mn) ? x : mn; }
-        scal[0] = mn;
+        scal[4] = mn;
+        if (also_scal0) scal[0] = mn;
     }
 }
 
