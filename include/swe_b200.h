@@ -190,13 +190,18 @@ SWE_API int swe_set_fluxer(swe_ctx *ctx, int32_t id);
 
 /* Switches for the places where upstream HEAD is unfinished. Defaults = the
  * repaired scheme; the alternatives reproduce upstream exactly as written and are bit-checked against
- * upstream's own sources compiled in oracle/_ref (tests/test_ref_anchor.py, tests/test_gpu_parity.py):
+ * upstream's own sources compiled by the test tree (tests/test_ref_anchor.py, tests/test_gpu_parity.py):
  *   "recon"   0 plane gradients of w,u,v from grad_values (S2, default) | 1 as written:
  *             src/MUSCLObject.cpp:63-64 df.row(0) = Gradient(grad_points), u/v first order | 2 first order
  *   "pw2"     0 ReconstructPartWetCell2 reads points(r,c) as (point, coordinate) (S3, default) |
  *             1 as written (src/MUSCLObject.cpp:141-183)
  *   "roe_fix" 0 Einfeldt Roe velocity cl*ur as written (src/Fluxes.cpp:22, default) | 1 cr*ur
- *   "cfl_abs" 0 HLLC CFL candidate max(tol, max(al, ar)) as written (include/Fluxes.h:89, default) | 1 magnitudes */
+ *   "cfl_abs" 0 HLLC CFL candidate max(tol, max(al, ar)) as written (include/Fluxes.h:89, default) | 1 magnitudes
+ * Tuning switches (identical bits either way; A/B evidence in profiles/README.md):
+ *   "graph"       -1 replay whole steps as a CUDA graph on meshes below 4M cells (default) | 0 off | 1 on
+ *   "k1_tiled"    0 register-prefetched gather reconstruction (default) | 1 TMA-staged shared-memory tiles
+ *   "fused_drain" 0 separate draining-dt pass (default) | 1 draining dt computed inside the stage update
+ *                 (swe_get_draining_dt then needs swe_enable_taps or swe_compute_rhs) */
 SWE_API int swe_set_option(swe_ctx *ctx, const char *key, int32_t value);
 SWE_API int swe_get_option(swe_ctx *ctx, const char *key, int32_t *value);
 /* Debug tap (taps enabled): how many cells took each branch in the last swe_compute_interface_values.

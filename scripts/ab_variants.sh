@@ -1,0 +1,9 @@
+B="python bench.py --no-cpu --no-thacker --no-repro --e2e-steps 2"
+P='import json,sys; d=json.load(open(sys.argv[1])); k=d["roofline"]["kernels"]; print(sys.argv[1], round(d["ms_per_step"],3), {a:round(b["ms_per_stage"],3) for a,b in k.items()}, d["clocks"]["sm_mhz"])'
+run() { name=$1; shift; env "$@" $B > gpurun_out/r2_ab_$name.json 2>gpurun_out/r2_ab_$name.err; python -c "$P" gpurun_out/r2_ab_$name.json; }
+run base A=1
+run k1b3 SWE_B200_LIB=$PWD/swe_fvm_b200/libswe_b200_k1b3.so
+run fmad SWE_B200_LIB=$PWD/swe_fvm_b200/libswe_b200_fmad.so
+run carve0 SWE_B200_CARVEOUT=0
+run carve25 SWE_B200_CARVEOUT=25
+run base2 A=1

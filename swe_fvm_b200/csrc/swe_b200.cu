@@ -22,6 +22,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 using namespace swe;
 
@@ -39,6 +41,15 @@ struct swe_ctx {
     int fluxer = -1;    // registry id selected by swe_set_fluxer (-1: use the (flux, wavespeed) enums of the call)
     int opt_tiled = 0;  // K1 form: 0 = register-prefetched gathers (default, faster: profiles/r2_k1_tiled_vs_gather.md), 1 = TMA-staged tiles
     unsigned long long *dbg = nullptr;                                 // branch-hit counters (taps)
+    // fused draining dt (k_update<.., FUSED>): K3 runs only over this static list of cells whose dti is read from
+    // global memory by a neighbour in another update tile / ordering class; 0 = separate k_drain pass over all cells.
+    // Off by default: measured SLOWER at 64M cells (profiles/README.md, r2_fused_drain_ab.json): 15-25 % of the cells
+    // sit on a 128-cell tile border, so the list pass costs 0.62 ms against 0.73 ms for the full pass, and the fused
+    // update needs 104 registers + a barrier (2.75 vs 2.23 ms)
+    int opt_fused_drain = 0;
+    int *drain_list = nullptr;
+    int drain_count = 0;
+    bool dti_complete = false;  // c->dti holds the draining dt of EVERY cell (full k_drain ran for the last stage)
     int class_first[6] = {0, 0, 0, 0, 0, 0};  // device cell range of every ordering class
     // device mesh
     int *tt = nullptr, *te = nullptr, *tp = nullptr, *slotL = nullptr, *slotR = nullptr;
@@ -226,7 +237,7 @@ static void destroy_ctx(swe_ctx *c) {
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
-                    c->send_cells, c->recv_cells, c->dbg};
+                    c->send_cells, c->recv_cells, c->dbg, c->drain_list};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
@@ -304,7 +315,9 @@ static void preload_kernels() {
 #define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>);
     SWE_FLUX_LIST(SWE_X)
 #undef SWE_X
-    SWE_LOAD(k_drain);
+    SWE_LOAD(k_drain); SWE_LOAD(k_drain_list);
+    SWE_LOAD(k_update<true, true, false, true>); SWE_LOAD(k_update<true, false, false, true>);
+    SWE_LOAD(k_update<false, true, false, true>); SWE_LOAD(k_update<false, false, false, true>);
     SWE_LOAD(k_update<true, true>); SWE_LOAD(k_update<true, false>); SWE_LOAD(k_update<false, true>); SWE_LOAD(k_update<false, false>);
     SWE_LOAD(k_update<true, true, true>); SWE_LOAD(k_update<true, false, true>); SWE_LOAD(k_classify);
     SWE_LOAD(k_post_step); SWE_LOAD(k_set_scalar);
@@ -313,6 +326,13 @@ static void preload_kernels() {
     SWE_LOAD(k_state_hash); SWE_LOAD(k_state_in); SWE_LOAD(k_state_out); SWE_LOAD(k_diag_partial); SWE_LOAD(k_diag_final);
 #undef SWE_LOAD_K1
 #undef SWE_LOAD
+    if (const char *e = std::getenv("SWE_B200_CARVEOUT")) {  // A/B: shared-memory carve-out (per cent) of the gather kernels
+        const int pct = std::atoi(e);
+        cudaFuncSetAttribute((const void *)k_reconstruct<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((const void *)k_flux<BuiltinFlux<1, 2>, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((const void *)k_update<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((const void *)k_update<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     cudaGetLastError();
 }
 
@@ -385,6 +405,9 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     c->device = device; c->nt = (int)nt; c->ne = (int)ne; c->nn = (int)nn; c->sms = sm_count;
     c->cor = mesh->cor; c->tau = mesh->tau;
     c->reordered = reorder != 0 || cell_class != nullptr;
+    // tuning defaults can be overridden from the environment for A/B runs (same switches as swe_set_option)
+    if (const char *e = std::getenv("SWE_B200_FUSED_DRAIN")) c->opt_fused_drain = std::atoi(e) != 0;
+    if (const char *e = std::getenv("SWE_B200_K1_TILED")) c->opt_tiled = (std::atoi(e) != 0 && SWE_K1_TILED) ? 1 : 0;
     if (cell_class)
         for (int64_t t = 0; t < nt; ++t)
             if (cell_class[t] > 3) { delete c; return fail(SWE_ERR_INVALID, "swe_create_classes: class ids must be 0..3"); }
@@ -584,6 +607,26 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0};  // [0] min_len, [1] dt, [2] time, [3] running min, [4] global min_len
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaDeviceSynchronize());
+    {   // K3' work list (fused draining dt): cells with a neighbour in another update tile or ordering class
+        unsigned char *flag = nullptr;
+        int *sel = nullptr, *d_cnt = nullptr;
+        void *tmp = nullptr;
+        size_t tb = 0;
+        ClassFirst cf;
+        for (int q = 0; q < 6; ++q) cf.f[q] = c->class_first[q];
+        CREATE_TRY(dalloc(&flag, (size_t)nt)); CREATE_TRY(dalloc(&sel, (size_t)nt)); CREATE_TRY(dalloc(&d_cnt, 1));
+        k_mark_drain_boundary<<<nblk(nt, 256), 256>>>(c->nt, c->tt, cf, flag);
+        CREATE_TRY(cudaGetLastError());
+        thrust::counting_iterator<int> ids(0);
+        CREATE_TRY(cub::DeviceSelect::Flagged(nullptr, tb, ids, flag, sel, d_cnt, (int)nt));
+        CREATE_TRY(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+        CREATE_TRY(cub::DeviceSelect::Flagged(tmp, tb, ids, flag, sel, d_cnt, (int)nt));
+        CREATE_TRY(cudaMemcpy(&c->drain_count, d_cnt, sizeof(int), cudaMemcpyDeviceToHost));
+        CREATE_TRY(dalloc(&c->drain_list, (size_t)c->drain_count));
+        CREATE_TRY(cudaMemcpy(c->drain_list, sel, sizeof(int) * (size_t)c->drain_count, cudaMemcpyDeviceToDevice));
+        cudaFree(tmp); cudaFree(flag); cudaFree(sel); cudaFree(d_cnt);
+        c->launches += 1;
+    }
 #undef CREATE_TRY
     *out = c;
     return SWE_OK;
@@ -757,7 +800,8 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "cfl_abs")) { if (value < 0 || value > 1) return bad("0 as written (signed max), 1 magnitudes"); c->opt_cfl_abs = value; }
     else if (!std::strcmp(key, "graph")) { if (value < -1 || value > 1) return bad("-1 auto, 0 off, 1 on"); c->opt_graph = value; }
     else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > SWE_K1_TILED) return bad("0 gather kernel, 1 shared-memory staged tiles"); c->opt_tiled = value; }
-    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, graph)");
+    else if (!std::strcmp(key, "fused_drain")) { if (value < 0 || value > 1) return bad("0 separate k_drain pass, 1 draining dt fused into the stage update"); c->opt_fused_drain = value; }
+    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, graph)");
     return SWE_OK;
 }
 SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
@@ -767,6 +811,7 @@ SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
     else if (!std::strcmp(key, "roe_fix")) *value = c->opt_roe_fix;
     else if (!std::strcmp(key, "cfl_abs")) *value = c->opt_cfl_abs;
     else if (!std::strcmp(key, "k1_tiled")) *value = c->opt_tiled;
+    else if (!std::strcmp(key, "fused_drain")) *value = c->opt_fused_drain;
     else if (!std::strcmp(key, "graph")) *value = c->opt_graph;
     else { c->err = std::string("swe_get_option: unknown option ") + key; return SWE_ERR_INVALID; }
     return SWE_OK;
@@ -894,7 +939,14 @@ static int stage_drain(swe_ctx *c, double ***outb_out) {
     const DevFields s = dev_fields(c);
     int rc;
     int kt = kt_begin(c, KT_DRAIN);
-    k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+    if (c->opt_fused_drain && !c->taps) {  // fused form: only the cells read across tile / class borders
+        if (c->drain_count > 0)
+            k_drain_list<<<std::min(nblk(c->drain_count, kBlock), c->sms * 16), kBlock, 0, c->stream>>>(m, s, c->drain_list, c->drain_count);
+        c->dti_complete = false;
+    } else {  // taps: swe_get_draining_dt wants every cell (the fused update still computes its own copy)
+        k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+        c->dti_complete = true;
+    }
     kt_end(c, kt);
     if ((rc = launch_check(c, "k_drain"))) return rc;
     double **outb = c->cur;
@@ -910,11 +962,16 @@ static int stage_update_range(swe_ctx *c, double **outb, double a0, double a1, d
     if (last <= first) return SWE_OK;
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
-    const int g = nblk(last - first, kBlock);
+    const bool fused = c->opt_fused_drain != 0;
+    // fused: one block per ABSOLUTE 128-cell tile touching [first, last)
+    const int g = fused ? ((last - 1) >> kUpdTileShift) - (first >> kUpdTileShift) + 1 : nblk(last - first, kBlock);
     const int kt = kt_begin(c, KT_UPDATE);
     const bool cor_on = c->cor != 0.;
 #define SWE_UPD(PLAIN, COR, W0, U0, V0) \
-    k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last)
+    do { \
+        if (fused) k_update<PLAIN, COR, false, true><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
+        else k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
+    } while (0)
     if (a0 == 0.) {
         if (cor_on) SWE_UPD(true, true, nullptr, nullptr, nullptr); else SWE_UPD(true, false, nullptr, nullptr, nullptr);
     } else {
@@ -1014,7 +1071,7 @@ static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespe
         return code;
     };
     const int fluxer = c->fluxer >= 0 ? c->fluxer : 3 * (int)flux + (int)ws;
-    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 5) | ((c->taps ? 1 : 0) << 6);
+    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 5) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7);
     for (int64_t s = 0; s < nsteps; ++s) {
         const int parity = (c->cur == c->bufA) ? 0 : 1;
         swe_ctx::StepGraph *g = nullptr;
@@ -1154,7 +1211,15 @@ SWE_API int swe_get_node_max_w(swe_ctx *c, double *out) {
     if ((rc = launch_check(c, "k_node_maxw_out"))) return rc;
     return tap_out(c, out, (size_t)c->nn);
 }
-SWE_API int swe_get_draining_dt(swe_ctx *c, double *out) { return c ? scalar_tap(c, out, c->dti, c->nt, c->cell_old) : SWE_ERR_INVALID; }
+SWE_API int swe_get_draining_dt(swe_ctx *c, double *out) {
+    if (!c) return SWE_ERR_INVALID;
+    if (!c->dti_complete) {
+        c->err = "swe_get_draining_dt: the fused stage update keeps the draining dt on chip; call swe_enable_taps(ctx, 1) before the "
+                 "stage, or swe_compute_rhs, to materialise it for every cell";
+        return SWE_ERR_INVALID;
+    }
+    return scalar_tap(c, out, c->dti, c->nt, c->cell_old);
+}
 SWE_API int swe_get_cell_class(swe_ctx *c, int8_t *out) {
     if (!c || !out) return SWE_ERR_INVALID;
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1208,6 +1273,7 @@ SWE_API int swe_compute_rhs(swe_ctx *c, double dt, double *rhs) {
     const DevFields s = dev_fields(c);
     k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
     if ((rc = launch_check(c, "k_drain"))) return rc;
+    c->dti_complete = true;
     double *r0 = c->stage_aos, *r1 = r0 + c->nt, *r2 = r1 + c->nt, *aos = r2 + c->nt;
     const int g = nblk(c->nt, kBlock);
     if (c->cor != 0.) k_update<true, true, true><<<g, kBlock, 0, c->stream>>>(m, s, nullptr, nullptr, nullptr, r0, r1, r2, 0., 1., dt, 0., c->cor, 0, c->nt);

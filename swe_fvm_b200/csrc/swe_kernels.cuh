@@ -53,7 +53,7 @@ struct DevFields {
     int recon;                       // S2: 0 repaired (w,u,v plane gradients), 1 as written upstream, 2 first order
     int pw2;                         // S3: 0 PartWet2 points(r,c) read as (point, coordinate), 1 as written
 };
-// branch-hit counter slots (same meaning as oracle/swe_oracle.cpp `branch`)
+// branch-hit counter slots (the CPU checker in the test tree keeps the same twelve counters)
 enum { BR_PW1_SUBMERGED = 0, BR_PW1_CBRT, BR_PW1_BISECTION, BR_FW_DRY_NB, BR_FW_PW_NB, BR_FW_VERTEX_ZERO, BR_FW_TVD_OFF,
        BR_PW2_TO_PW1, BR_PW2_ONE_WET, BR_PW2_THREE_WET, BR_PW2_TWO_WET, BR_PW2_FALLBACK, BR_COUNT };
 template <bool TAPS> __device__ __forceinline__ void count_branch(const DevFields &s, int b) {
@@ -125,10 +125,22 @@ constexpr int kK1Block = SWE_K1_BLOCK;
 #ifndef SWE_K1_GRID_PER_SM
 #define SWE_K1_GRID_PER_SM 4
 #endif
-__device__ __forceinline__ double4 ldg4(const double4 *p) {  // 32-byte read-only gather
+// 32-byte read-only gather of one geometry packet. sm_100 has 256-bit global loads (ld.global.nc.v4.f64 ->
+// LDG.E.ENL2.256.CONSTANT): one instruction and one L1 request per packet instead of two 128-bit ones. The packet
+// arrays come from cudaMalloc and hold 32-byte elements, so every element is 32-byte aligned.
+#ifndef SWE_LD256
+#define SWE_LD256 1
+#endif
+__device__ __forceinline__ double4 ldg4(const double4 *p) {
+#if SWE_LD256
+    double4 r;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+#else
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
     const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
     return make_double4(a.x, a.y, b.x, b.y);
+#endif
 }
 template <bool TAPS>
 __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFields &s, const int i, const int ip0,
@@ -727,6 +739,46 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
     st_once(s.dti + i, r);
 }
 
+// K3', the list-driven form used with the fused stage update: only the cells whose draining dt is read from
+// global memory by some neighbour — cells with a neighbour in another 128-cell update tile or in another
+// ordering class (a static list built at set-up, a few per cent of the mesh). Same arithmetic as k_drain.
+__device__ __forceinline__ double drain_dt_cell(double h, double area, double fe0, double fe1, double fe2) {
+    if (!is_wet(h)) return 0.;
+    double sum = 0.;
+    sum += smax(0., fe0); sum += smax(0., fe1); sum += smax(0., fe2);
+    return (sum > kTol) ? area * h / sum : __longlong_as_double(0x7ff0000000000000ll);
+}
+__global__ void __launch_bounds__(kBlock) k_drain_list(DevMesh m, DevFields s, const int *__restrict__ list, int n) {
+    const int nt = m.nt;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int i = __ldg(list + q);
+        const int t0 = __ldg(m.te + i), t1 = __ldg(m.te + nt + i), t2 = __ldg(m.te + 2 * nt + i);
+        const double fe0 = (t0 >= 0) ? s.f0[t0] : -s.f0[~t0];
+        const double fe1 = (t1 >= 0) ? s.f0[t1] : -s.f0[~t1];
+        const double fe2 = (t2 >= 0) ? s.f0[t2] : -s.f0[~t2];
+        s.dti[i] = drain_dt_cell(s.w[i] - m.cb[i], m.area[i], fe0, fe1, fe2);
+    }
+}
+// set-up: flag the cells of the K3' list. cf[q] = first device id of ordering class q (classes are contiguous).
+struct ClassFirst { int f[6]; };
+__device__ __forceinline__ int class_of(const ClassFirst &cf, int i) {
+    return (i >= cf.f[1]) + (i >= cf.f[2]) + (i >= cf.f[3]) + (i >= cf.f[4]);
+}
+constexpr int kUpdTileShift = 7;  // the stage update works on tiles of kBlock = 128 consecutive cells
+static_assert((1 << kUpdTileShift) == kBlock, "update tile = one thread block");
+__global__ void k_mark_drain_boundary(int nt, const int *tt, ClassFirst cf, unsigned char *flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const int ci = class_of(cf, i), ti = i >> kUpdTileShift;
+    bool b = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int j = tt[k * nt + i];
+        if (j >= 0 && ((j >> kUpdTileShift) != ti || class_of(cf, j) != ci)) b = true;
+    }
+    flag[i] = b ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // K4: RHS gather (src/TimeDisc.cpp:3-41) + RK combination (src/Solvers.cpp) + ConsAssigner
 // (src/Assigners.cpp:22-44). Deterministic: fixed k order, no float atomics.
@@ -738,14 +790,24 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
 #define SWE_K4_MIN_BLOCKS 1
 #endif
 // RHS_ONLY (tap for TimeDisc::RHS(i, dt)): store the increment (r0, r1, r2) instead of applying it.
-template <bool PLAIN, bool COR, bool RHS_ONLY = false>
+// FUSED: the draining dt (K3, src/TimeDisc.cpp:43-66) of the block's own cells is computed here from the already
+// loaded mass fluxes and shared through shared memory; blocks work on ABSOLUTE 128-cell tiles, so a neighbour in the
+// same tile (and inside [first, last)) is served from shared memory and only the few neighbours outside read the
+// global dti array, which k_drain_list filled for exactly those cells. Saves the k_drain pass over all cells and
+// three 8-byte gathers per cell.
+template <bool PLAIN, bool COR, bool RHS_ONLY = false, bool FUSED = false>
 __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m, DevFields s, const double *__restrict__ w0,
                                                    const double *__restrict__ u0, const double *__restrict__ v0,
                                                    double *wout, double *uout, double *vout, double a0, double a1,
                                                    double dt_host, double dt_coef, double cor, int first, int last) {
-    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;  // cell range [first, last) in device numbering
+    // cell range [first, last) in device numbering; FUSED: tiles on absolute kBlock boundaries
+    const int base = FUSED ? ((first >> kUpdTileShift) + (int)blockIdx.x) << kUpdTileShift : first + blockIdx.x * blockDim.x;
+    int i = base + threadIdx.x;
     const int nt = m.nt;
-    if (i >= last) return;
+    __shared__ double sdt[FUSED ? kBlock : 1];
+    const bool active = FUSED ? (i >= first && i < last) : true;
+    if (!FUSED) { if (i >= last) return; }
+    else if (!active) i = first;  // idle lanes of a partial tile shadow a valid cell (loads stay in bounds), never store
     // All loads are issued before any arithmetic (ids -> gathers: two dependent round trips, every
     // gather of the cell in flight at once). Written out explicitly because the compiler's own
     // schedule flipped between a batched (2.2 ms) and an interleaved (2.6 ms at 64M cells) form
@@ -757,22 +819,37 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     const double dt = (dt_coef != 0.) ? dt_coef * s.scal[1] : dt_host;
     const double cb = __ldg(m.cb + i);
     const double area_i = __ldg(m.area + i);
-    const double dti = s.dti[i];
+    double dti = FUSED ? 0. : s.dti[i];
     const double gx = s.cgx[i], gy = s.cgy[i];
     const double wc = s.w[i], uc = s.u[i], vc = s.v[i];
     double wa = 0., ua = 0., va = 0.;
     if (!PLAIN) { wa = w0[i]; ua = u0[i]; va = v0[i]; }
     double F0[3], F1[3], F2[3], dtn[3], len[3], hek[3], cu[3], cv[3];
     double2 nrm[3];
+    const int lo_t = max(base, first), hi_t = min(base + kBlock, last);  // FUSED: cells whose dti this block computes
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int e = te[k] >= 0 ? te[k] : ~te[k];
         F0[k] = s.f0[e]; F1[k] = s.f1[e]; F2[k] = s.f2[e];
-        dtn[k] = (tn[k] < 0) ? __longlong_as_double(0x7ff0000000000000ll) : s.dti[tn[k]];
+        if (FUSED) {  // in-tile neighbours come from shared memory after the barrier below
+            const bool in_tile = tn[k] >= lo_t && tn[k] < hi_t;
+            dtn[k] = (tn[k] < 0) ? __longlong_as_double(0x7ff0000000000000ll) : (in_tile ? 0. : s.dti[tn[k]]);
+        } else {
+            dtn[k] = (tn[k] < 0) ? __longlong_as_double(0x7ff0000000000000ll) : s.dti[tn[k]];
+        }
         len[k] = __ldg(m.elen + e);
         nrm[k] = __ldg(m.en + e);
         hek[k] = s.ceh[k * nt + i];
         if (COR) { cu[k] = s.ceu[k * nt + i]; cv[k] = s.cev[k * nt + i]; }
+    }
+    if (FUSED) {
+        dti = drain_dt_cell(wc - cb, area_i, te[0] >= 0 ? F0[0] : -F0[0], te[1] >= 0 ? F0[1] : -F0[1], te[2] >= 0 ? F0[2] : -F0[2]);
+        sdt[threadIdx.x] = dti;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (tn[k] >= lo_t && tn[k] < hi_t) dtn[k] = sdt[tn[k] - base];
+        if (!active) return;
     }
     const double i_area = 1. / area_i;
     double r0 = 0., r1 = 0., r2 = 0.;

@@ -296,6 +296,37 @@ def test_cuda_graph_replay_equals_plain_launches(cases, scheme):
     assert out[0][3] == out[1][3]  # the graph path reports the kernels it replays
 
 
+@pytest.mark.parametrize("name", ["thacker64", "bowl_hump", "lake71"])
+@pytest.mark.parametrize("reorder", [False, True])
+def test_fused_draining_dt_equals_separate_pass_and_oracle(cases, name, reorder):
+    """The stage update computes the draining dt of its own 128-cell tile on chip (shared memory) and reads only the
+    cells across tile borders from the list-driven K3': same bits as the separate k_drain pass and as the oracle,
+    with and without taps, on wet/dry fronts (draining cells) and with Coriolis."""
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    from oracle.oracle import Oracle
+    mesh, case, v0 = cases[name]
+    ref = Oracle(mesh, cor=0.2)
+    ref.set_state(v0)
+    sds = []
+    for fused, taps in ((1, False), (0, False), (1, True)):
+        sd = SpaceDisc("hllc", "einfeldt", mesh, v0, cor=0.2, reorder=reorder, taps=taps)
+        sd.set_option("fused_drain", fused)
+        sd.set_option("graph", 0)
+        assert sd.get_option("fused_drain") == fused
+        sds.append((sd, TimeDisc(sd)))
+    for k in range(6):
+        ref.step(2, 1, 2, 2e-3)
+        for sd, td in sds:
+            Solvers.SSPRK3(td, 2e-3)
+            np.testing.assert_array_equal(sd.GetVolField(), ref.get_state())
+    # the tap is only available when every cell's value was materialised
+    with pytest.raises(Exception, match="fused stage update"):
+        sds[0][0].draining_dt()
+    sds[2][0].draining_dt()
+    sds[0][0].rhs(1e-3)
+    sds[0][0].draining_dt()
+
+
 def test_create_rejects_another_local_edge_order():
     """swe_create validates the local convention the kernels rely on (edge k joins nodes k, k+1; neighbour k across it)."""
     from swe_fvm_b200 import StructTriangMesh, SweError
