@@ -1,9 +1,9 @@
+#!/bin/bash
+# A/B runs of tuning variants on one box (same process environment, back to back): prints ms/step and ms/stage per kernel.
 B="python bench.py --no-cpu --no-thacker --no-repro --e2e-steps 2"
 P='import json,sys; d=json.load(open(sys.argv[1])); k=d["roofline"]["kernels"]; print(sys.argv[1], round(d["ms_per_step"],3), {a:round(b["ms_per_stage"],3) for a,b in k.items()}, d["clocks"]["sm_mhz"])'
-run() { name=$1; shift; env "$@" $B > gpurun_out/r2_ab_$name.json 2>gpurun_out/r2_ab_$name.err; python -c "$P" gpurun_out/r2_ab_$name.json; }
+run() { name=$1; shift; env "$@" $B > gpurun_out/r2_ab_$name.json 2>gpurun_out/r2_ab_$name.err; python -c "$P" gpurun_out/r2_ab_$name.json || tail -3 gpurun_out/r2_ab_$name.err; }
 run base A=1
-run k1b3 SWE_B200_LIB=$PWD/swe_fvm_b200/libswe_b200_k1b3.so
-run fmad SWE_B200_LIB=$PWD/swe_fvm_b200/libswe_b200_fmad.so
-run carve0 SWE_B200_CARVEOUT=0
-run carve25 SWE_B200_CARVEOUT=25
+run k3np SWE_B200_LIB=$PWD/swe_fvm_b200/libswe_b200_k3np.so
+run k3g8 SWE_B200_LIB=$PWD/swe_fvm_b200/libswe_b200_k3g8.so
 run base2 A=1

@@ -168,6 +168,13 @@ static DevFields dev_fields(const swe_ctx *c) {
 template <class T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
+static inline int drain_grid(const swe_ctx *c) {
+#if SWE_K3_PERSISTENT
+    return std::min(nblk(c->nt, kBlock), c->sms * SWE_K3_GRID_PER_SM);
+#else
+    return nblk(c->nt, kBlock);
+#endif
+}
 static int launch_check(swe_ctx *c, const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { c->err = std::string(what) + ": " + cudaGetErrorString(e); return SWE_ERR_CUDA; }
@@ -310,6 +317,7 @@ static void preload_kernels() {
 #define SWE_LOAD(...) cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__))
 #define SWE_LOAD_K1(T) SWE_LOAD(k_reconstruct<T, 0>); SWE_LOAD(k_reconstruct<T, 1>); SWE_LOAD(k_reconstruct<T, 2>); \
     SWE_LOAD(k_reconstruct_tiled<T, 0>); SWE_LOAD(k_reconstruct_tiled<T, 1>); SWE_LOAD(k_reconstruct_tiled<T, 2>); \
+    SWE_LOAD(k_reconstruct_pf<T, 0>); SWE_LOAD(k_reconstruct_pf<T, 1>); SWE_LOAD(k_reconstruct_pf<T, 2>); \
     SWE_LOAD(k_reconstruct_slow<T>); SWE_LOAD(k_partwet2<T>)
     SWE_LOAD_K1(false); SWE_LOAD_K1(true);
 #define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>);
@@ -407,7 +415,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     c->reordered = reorder != 0 || cell_class != nullptr;
     // tuning defaults can be overridden from the environment for A/B runs (same switches as swe_set_option)
     if (const char *e = std::getenv("SWE_B200_FUSED_DRAIN")) c->opt_fused_drain = std::atoi(e) != 0;
-    if (const char *e = std::getenv("SWE_B200_K1_TILED")) c->opt_tiled = (std::atoi(e) != 0 && SWE_K1_TILED) ? 1 : 0;
+    if (const char *e = std::getenv("SWE_B200_K1_TILED")) c->opt_tiled = SWE_K1_TILED ? std::min(2, std::max(0, std::atoi(e))) : 0;
     if (cell_class)
         for (int64_t t = 0; t < nt; ++t)
             if (cell_class[t] > 3) { delete c; return fail(SWE_ERR_INVALID, "swe_create_classes: class ids must be 0..3"); }
@@ -799,7 +807,7 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "roe_fix")) { if (value < 0 || value > 1) return bad("0 as written (cl*ur), 1 cr*ur"); c->opt_roe_fix = value; }
     else if (!std::strcmp(key, "cfl_abs")) { if (value < 0 || value > 1) return bad("0 as written (signed max), 1 magnitudes"); c->opt_cfl_abs = value; }
     else if (!std::strcmp(key, "graph")) { if (value < -1 || value > 1) return bad("-1 auto, 0 off, 1 on"); c->opt_graph = value; }
-    else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > SWE_K1_TILED) return bad("0 gather kernel, 1 shared-memory staged tiles"); c->opt_tiled = value; }
+    else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > 2 * SWE_K1_TILED) return bad("0 gather kernel, 1 TMA-staged shared-memory tiles, 2 cp.async software pipeline"); c->opt_tiled = value; }
     else if (!std::strcmp(key, "fused_drain")) { if (value < 0 || value > 1) return bad("0 separate k_drain pass, 1 draining dt fused into the stage update"); c->opt_fused_drain = value; }
     else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, graph)");
     return SWE_OK;
@@ -850,7 +858,11 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         const int gt = std::min(ntiles, c->sms * SWE_K1_GRID_PER_SM);
 #define SWE_K1(TAPS) \
         do { \
-            if (c->opt_tiled) { \
+            if (c->opt_tiled == 2) { \
+                if (c->opt_recon == 0) k_reconstruct_pf<TAPS, 0><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+                else if (c->opt_recon == 1) k_reconstruct_pf<TAPS, 1><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+                else k_reconstruct_pf<TAPS, 2><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+            } else if (c->opt_tiled) { \
                 if (c->opt_recon == 0) k_reconstruct_tiled<TAPS, 0><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
                 else if (c->opt_recon == 1) k_reconstruct_tiled<TAPS, 1><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
                 else k_reconstruct_tiled<TAPS, 2><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
@@ -944,7 +956,7 @@ static int stage_drain(swe_ctx *c, double ***outb_out) {
             k_drain_list<<<std::min(nblk(c->drain_count, kBlock), c->sms * 16), kBlock, 0, c->stream>>>(m, s, c->drain_list, c->drain_count);
         c->dti_complete = false;
     } else {  // taps: swe_get_draining_dt wants every cell (the fused update still computes its own copy)
-        k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+        k_drain<<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
         c->dti_complete = true;
     }
     kt_end(c, kt);
@@ -1071,7 +1083,7 @@ static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespe
         return code;
     };
     const int fluxer = c->fluxer >= 0 ? c->fluxer : 3 * (int)flux + (int)ws;
-    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 5) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7);
+    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7);
     for (int64_t s = 0; s < nsteps; ++s) {
         const int parity = (c->cur == c->bufA) ? 0 : 1;
         swe_ctx::StepGraph *g = nullptr;
@@ -1271,7 +1283,7 @@ SWE_API int swe_compute_rhs(swe_ctx *c, double dt, double *rhs) {
     if (rc) return rc;
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
-    k_drain<<<nblk(c->nt, kBlock), kBlock, 0, c->stream>>>(m, s);
+    k_drain<<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
     if ((rc = launch_check(c, "k_drain"))) return rc;
     c->dti_complete = true;
     double *r0 = c->stage_aos, *r1 = r0 + c->nt, *r2 = r1 + c->nt, *aos = r2 + c->nt;

@@ -527,6 +527,103 @@ __global__ void __launch_bounds__(kTile, SWE_K1_MIN_BLOCKS) k_reconstruct_tiled(
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K1, software-pipelined form (k1_tiled = 2): every thread copies the inputs of its NEXT cell — own packet and
+// state, the three node packets, the three neighbour packets and states: 26 cp.async (LDGSTS, through L1) of 8 or 16
+// bytes — into its private column of a shared-memory stage while it computes the current cell, so the ~1 us memory
+// round trip that the gather kernel exposes once per cell (ncu: long-scoreboard = half of all warp cycles, fp64
+// pipe 43 %, DRAM 62 %) is hidden behind ~550 instructions of arithmetic. The stage is single-buffered: a cell's
+// values are moved to registers first, then the copies of the next cell are issued into the same slots (same thread,
+// program order). 296 bytes per thread = 37 KB per 128-thread block, structure-of-arrays so that both the 8- and
+// the 16-byte accesses of a warp are bank-conflict free. No block barrier: a thread only ever touches its own slots.
+// ---------------------------------------------------------------------------------------
+struct K1Pf {
+    double2 pxy[3][kK1Block];   // node packets (x, y)
+    double2 ga[4][kK1Block];    // cgeo (cx, cy): neighbours 0-2, own cell 3
+    double2 gb[4][kK1Block];    // cgeo (cb, bfull)
+    double pz[3][kK1Block];     // node bed
+    double st[12][kK1Block];    // w,u,v of neighbours 0-2 (3k + c), own cell 9-11
+};
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void k1pf_issue(const DevMesh &m, const DevFields &s, K1Pf &st, const int tid, const int i, const int ip0,
+                                           const int ip1, const int ip2, const int it0, const int it1, const int it2) {
+    const int ip[3] = {ip0, ip1, ip2};
+    const int jt[4] = {max(it0, 0), max(it1, 0), max(it2, 0), i};  // boundary sides: clamped, values never used
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double *np = reinterpret_cast<const double *>(m.node + ip[k]);
+        cp_async16(&st.pxy[k][tid], np);
+        cp_async8(&st.pz[k][tid], np + 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double *gp = reinterpret_cast<const double *>(m.cgeo + jt[k]);
+        cp_async16(&st.ga[k][tid], gp);
+        cp_async16(&st.gb[k][tid], gp + 2);
+        cp_async8(&st.st[3 * k][tid], s.w + jt[k]);
+        cp_async8(&st.st[3 * k + 1][tid], s.u + jt[k]);
+        cp_async8(&st.st[3 * k + 2][tid], s.v + jt[k]);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <bool TAPS, int RECON>
+__global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct_pf(DevMesh m, DevFields s, int first, int last) {
+    __shared__ K1Pf st;
+    const int nt = m.nt;
+    const int tid = threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    int i = first + blockIdx.x * blockDim.x + tid;
+    if (i >= last) return;
+    int it0, it1, it2;
+    {
+        const int ip0 = __ldg(m.tp + i), ip1 = __ldg(m.tp + nt + i), ip2 = __ldg(m.tp + 2 * nt + i);
+        it0 = __ldg(m.tt + i); it1 = __ldg(m.tt + nt + i); it2 = __ldg(m.tt + 2 * nt + i);
+        k1pf_issue(m, s, st, tid, i, ip0, ip1, ip2, it0, it1, it2);
+    }
+    // ids of the next cell (consumed when its copies are issued, one iteration from now)
+    int nx = i + stride;
+    int np0 = 0, np1 = 0, np2 = 0, nt0 = 0, nt1 = 0, nt2 = 0;
+    if (nx < last) {
+        np0 = __ldg(m.tp + nx); np1 = __ldg(m.tp + nt + nx); np2 = __ldg(m.tp + 2 * nt + nx);
+        nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
+    }
+    for (;;) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        double2 a, b;
+        a = st.pxy[0][tid]; const double4 P0 = make_double4(a.x, a.y, st.pz[0][tid], 0.);
+        a = st.pxy[1][tid]; const double4 P1 = make_double4(a.x, a.y, st.pz[1][tid], 0.);
+        a = st.pxy[2][tid]; const double4 P2 = make_double4(a.x, a.y, st.pz[2][tid], 0.);
+        a = st.ga[0][tid]; b = st.gb[0][tid]; const double4 G0 = make_double4(a.x, a.y, b.x, b.y);
+        a = st.ga[1][tid]; b = st.gb[1][tid]; const double4 G1 = make_double4(a.x, a.y, b.x, b.y);
+        a = st.ga[2][tid]; b = st.gb[2][tid]; const double4 G2 = make_double4(a.x, a.y, b.x, b.y);
+        a = st.ga[3][tid]; b = st.gb[3][tid]; const double4 Gi = make_double4(a.x, a.y, b.x, b.y);
+        const double N00 = st.st[0][tid], N01 = st.st[1][tid], N02 = st.st[2][tid];
+        const double N10 = st.st[3][tid], N11 = st.st[4][tid], N12 = st.st[5][tid];
+        const double N20 = st.st[6][tid], N21 = st.st[7][tid], N22 = st.st[8][tid];
+        const double w = st.st[9][tid], u = st.st[10][tid], v = st.st[11][tid];
+        const bool bnd = (it0 | it1 | it2) < 0;
+        const bool more = nx < last;
+        if (more) {  // the slots are free again: start the copies of the next cell, then fetch the ids of the one after
+            k1pf_issue(m, s, st, tid, nx, np0, np1, np2, nt0, nt1, nt2);
+            it0 = nt0; it1 = nt1; it2 = nt2;
+            const int n2 = nx + stride;
+            if (n2 < last) {
+                np0 = __ldg(m.tp + n2); np1 = __ldg(m.tp + nt + n2); np2 = __ldg(m.tp + 2 * nt + n2);
+                nt0 = __ldg(m.tt + n2); nt1 = __ldg(m.tt + nt + n2); nt2 = __ldg(m.tt + 2 * nt + n2);
+            }
+        }
+        if (!fast_compute<TAPS, RECON>(s, nt, i, bnd, P0, P1, P2, Gi, w, u, v, N00, N01, N02, N10, N11, N12, N20, N21, N22, G0, G1, G2))
+            s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
+        if (!more) break;
+        i = nx; nx = i + stride;
+    }
+}
+
 // Value at node Q = (qx, qy, qz) of cell t's PASS-1 reconstruction, i.e. one term of the max in
 // m_max_wp[node] = max(m_max_wp[node], muscl.AtPoint(P(node))[0]) (src/SpaceDisc.cpp:23).
 __device__ __noinline__ double pass1_w_at_node(const DevMesh &m, const DevFields &s, int t, double qx, double qy, double qz) {
@@ -718,9 +815,34 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
 // ---------------------------------------------------------------------------------------
 // K3: draining time step (src/TimeDisc.cpp:43-66) of every cell from the stage-begin state
 // ---------------------------------------------------------------------------------------
+#ifndef SWE_K3_PERSISTENT
+#define SWE_K3_PERSISTENT 0  // measured: 0.905 ms persistent vs 0.716 ms one cell per short-lived thread at 64M cells
+#endif
+#ifndef SWE_K3_GRID_PER_SM
+#define SWE_K3_GRID_PER_SM 16
+#endif
+__device__ __forceinline__ double drain_dt_cell(double h, double area, double fe0, double fe1, double fe2);
 __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nt = m.nt;
+#if SWE_K3_PERSISTENT
+    // persistent grid-stride form: the edge ids of the thread's next cell are fetched while the current cell waits
+    // for its flux gathers, so only one memory round trip per cell is exposed instead of two per short-lived thread
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    int t0 = __ldg(m.te + i), t1 = __ldg(m.te + nt + i), t2 = __ldg(m.te + 2 * nt + i);
+    for (;;) {
+        const int nx = i + stride;
+        int n0 = 0, n1 = 0, n2 = 0;
+        if (nx < nt) { n0 = __ldg(m.te + nx); n1 = __ldg(m.te + nt + nx); n2 = __ldg(m.te + 2 * nt + nx); }
+        const double f0 = s.f0[t0 >= 0 ? t0 : ~t0], f1 = s.f0[t1 >= 0 ? t1 : ~t1], f2 = s.f0[t2 >= 0 ? t2 : ~t2];
+        const double h = s.w[i] - m.cb[i];
+        st_once(s.dti + i, drain_dt_cell(h, m.area[i], t0 >= 0 ? f0 : -f0, t1 >= 0 ? f1 : -f1, t2 >= 0 ? f2 : -f2));
+        if (nx >= nt) break;
+        i = nx; t0 = n0; t1 = n1; t2 = n2;
+    }
+#else
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
     const double h = s.w[i] - m.cb[i];
     double r;
@@ -737,6 +859,7 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
         r = (sum > kTol) ? m.area[i] * h / sum : __longlong_as_double(0x7ff0000000000000ll);
     }
     st_once(s.dti + i, r);
+#endif
 }
 
 // K3', the list-driven form used with the fused stage update: only the cells whose draining dt is read from
