@@ -295,13 +295,16 @@ def run_gpu(args):
     length_y = nj * h
     if world == 1:
         mesh = StructTriangMesh(ni, nj, h)
+        t_mesh = time.perf_counter() - t_setup
         sd = SpaceDisc("hllc", "einfeldt", mesh, None, device=local_rank, reorder=args.reorder)
         n_owned = mesh.nt
     else:
         plan = swd.Plan.struct(rank, world, ni, nj, h)
+        t_mesh = time.perf_counter() - t_setup
         mesh, n_owned = plan.mesh, plan.n_owned
         ds = swd.DistSolver(plan, device=local_rank, reorder=args.reorder, overlap=not args.no_overlap)
         sd = ds.sd
+    t_create = time.perf_counter() - t_setup - t_mesh
     sd.set_stream(torch.cuda.current_stream().cuda_stream)
     for kv in args.opt:
         k, v = kv.split("=")
@@ -489,7 +492,7 @@ def run_gpu(args):
                        f"{world} strips behind the swe_dist_* C-ABI, 3-row halo, peer-memory stores over NVLink (CUDA IPC) fused into the "
                        f"stage ({'boundary cells updated first, stores overlap the interior update + reconstruction' if not args.no_overlap else 'not overlapped'}), "
                        f"peer-memory min all-reduce"),
-                   "dt": "CFLdt of the previous step (device resident)", "setup_s": t_setup,
+                   "dt": "CFLdt of the previous step (device resident)", "setup_s": t_setup, "setup_breakdown_s": {"host_mesh": t_mesh, "create_context": t_create, "case_on_device": t_setup - t_mesh - t_create},
                    "initial_state": "device-side TriangAverage<3,1> of the analytic case",
                    "device_numbering": "hilbert" if args.reorder else "caller"},
         "clocks": clocks,

@@ -5,13 +5,18 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it;
 // the product (swe_fvm_b200/, include/) never does.
 //
-// PARITY STATUS: the upstream tree does not build (Eigen not vendored, HEAD mid-refactor:
-// SURVEY.md §0 F2/F3/F6) and its only committed outputs pin the mesh numbering and the
-// initial condition exactly (notebooks/topology.dat, out0.dat) but the one-step result only
-// coarsely (notebooks/out1.dat, print precision, produced by an intermediate revision).
-// => "parity unpinned" for the step itself beyond that coarse check; this file follows the
-// reference sources function by function (citations below, paths relative to upstream) with
-// the semantic decisions S1-S10 of SURVEY.md App. A.10, each selectable by an option.
+// PARITY STATUS: PINNED. upstream's own src/*.cpp are compiled (oracle/Makefile.ref, Eigen subset shim
+// oracle/eigen_shim, named repairs in oracle/ref_patches/) into oracle/_ref/, and tests/test_ref_anchor.py
+// demands BIT equality between that code and this file — function by function (Gradient, Bisection,
+// ElemFlux, wavespeeds, assigners, Domain geometry, every reconstruction, fluxes, RHS, draining dt,
+// TriangAverage) and over whole Solvers::Euler/SSPRK2/SSPRK3 steps — in the modes recon/pw2 = as written
+// and repaired, libm=1, sequential=1. The DEFAULT mode differs from upstream only by the listed decisions
+// S7/S8 (stage snapshot instead of order-dependent in-place loops; checked against upstream's own RHS
+// applied out of place) and S9 (cbrt / (int)log2 restated with IEEE-only arithmetic, <= 1 ulp). The
+// reference's committed outputs pin the mesh numbering and the initial condition exactly
+// (notebooks/topology.dat, out0.dat) and the one-step result coarsely (out1.dat, print precision,
+// written by an intermediate upstream revision). Citations below are paths relative to upstream; the
+// semantic decisions S1-S11 of SURVEY.md App. A.10 are each selectable by an option.
 //
 // Arithmetic: build with `g++ -O2 -ffp-contract=off` on x86-64 (SSE2 doubles, no x87, no FMA),
 // so every expression below is evaluated in the written order in IEEE binary64; the CUDA

@@ -287,7 +287,7 @@ int read_gmsh(swe_hostmesh &m, const char *path) {
         m.geom[3 * p + 2] = 0.0;  // bathymetry set by the caller (Domain::AtNode upstream)
     }
     m.nt = (int64_t)tris.size() / 3;
-    m.tp = tris;
+    m.tp.assign(tris.begin(), tris.end());
     // enforce CCW (all CCW in gmsh output; flip defensively, keeping the first node)
     for (int64_t t = 0; t < m.nt; ++t) {
         const double *a = &m.geom[3 * m.tp[3 * t]], *b = &m.geom[3 * m.tp[3 * t + 1]], *c = &m.geom[3 * m.tp[3 * t + 2]];

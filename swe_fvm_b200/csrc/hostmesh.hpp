@@ -3,16 +3,34 @@
 // the cause of the dangling pybind binding) this object owns its arrays.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/swe_b200.h"
 
+namespace swe {
+// std::vector whose resize() leaves new elements uninitialised: the big mesh arrays are filled by OpenMP loops right
+// after the resize, and a value-initialising resize would first zero ~10 GB on ONE thread (2 s at 64M cells) and
+// place every page on that thread's NUMA node.
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+using dvec = std::vector<double, default_init_allocator<double>>;
+using ivec = std::vector<int64_t, default_init_allocator<int64_t>>;
+}  // namespace swe
+
 struct swe_hostmesh {
     int64_t nn = 0, ne = 0, nt = 0;
-    std::vector<double> geom;        // 3 x nn column-major (x, y, b)
-    std::vector<int64_t> ep, et;     // ne x 2
-    std::vector<int64_t> tp, te, tt; // nt x 3
+    swe::dvec geom;        // 3 x nn column-major (x, y, b)
+    swe::ivec ep, et;      // ne x 2
+    swe::ivec tp, te, tt;  // nt x 3
     // filled by swe_hostmesh_extract only
     std::vector<int64_t> global_cells, global_edges;
     std::vector<int32_t> owner;

@@ -6,6 +6,7 @@
 // edge-side reconstructions, fluxes, node maxima and draining time steps. Every C function
 // returns a status; nothing throws across the boundary. There is no CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -182,61 +183,6 @@ static int launch_check(swe_ctx *c, const char *what) {
     return SWE_OK;
 }
 
-// Hilbert-curve index of a point on the 2^21 x 2^21 grid (locality-preserving renumbering; no
-// quadrant jumps, unlike the Z-order / Morton curve)
-static inline uint64_t hilbert21(uint64_t x, uint64_t y) {
-    const uint64_t n = 1ull << 21;
-    uint64_t d = 0;
-    for (uint64_t s = n >> 1; s > 0; s >>= 1) {
-        const uint64_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
-        d += s * s * ((3 * rx) ^ ry);
-        if (ry == 0) {
-            if (rx == 1) { x = n - 1 - x; y = n - 1 - y; }
-            const uint64_t t = x; x = y; y = t;
-        }
-    }
-    return d;
-}
-// Space-filling-curve order of n points: keys are built on the host (OpenMP), the stable key sort runs on the
-// device (CUB radix sort, set-up only; ties keep the caller's order, so the result is the same
-// as a host std::sort of (key, index) pairs). newid[old] = position in Morton order.
-static cudaError_t morton_order(const std::vector<double> &x, const std::vector<double> &y, double x0, double y0,
-                                double sx, double sy, std::vector<int> &newid, const uint8_t *cls = nullptr,
-                                bool curve = true) {
-    const size_t n = x.size();
-    std::vector<uint64_t> keys(n);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-    for (int64_t i = 0; i < (int64_t)n; ++i) {
-        uint64_t qx = (uint64_t)std::min(2097151.0, std::max(0.0, (x[i] - x0) * sx));
-        uint64_t qy = (uint64_t)std::min(2097151.0, std::max(0.0, (y[i] - y0) * sy));
-        keys[i] = curve ? hilbert21(qx, qy) : (uint64_t)i;  // curve off: keep the caller's order inside a class
-        if (cls) keys[i] |= (uint64_t)cls[i] << 42;
-    }
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    uint64_t *dk_in = nullptr, *dk_out = nullptr;
-    int *dv_in = nullptr, *dv_out = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    cudaError_t e = cudaSuccess;
-    auto cleanup = [&]() { cudaFree(dk_in); cudaFree(dk_out); cudaFree(dv_in); cudaFree(dv_out); cudaFree(tmp); };
-#define MO_TRY(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
-    MO_TRY(cudaMalloc(&dk_in, n * 8)); MO_TRY(cudaMalloc(&dk_out, n * 8));
-    MO_TRY(cudaMalloc(&dv_in, n * 4)); MO_TRY(cudaMalloc(&dv_out, n * 4));
-    MO_TRY(cudaMemcpy(dk_in, keys.data(), n * 8, cudaMemcpyHostToDevice));
-    MO_TRY(cudaMemcpy(dv_in, order.data(), n * 4, cudaMemcpyHostToDevice));
-    MO_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 45));
-    MO_TRY(cudaMalloc(&tmp, tmp_bytes));
-    MO_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk_in, dk_out, dv_in, dv_out, (int64_t)n, 0, 45));
-    MO_TRY(cudaMemcpy(order.data(), dv_out, n * 4, cudaMemcpyDeviceToHost));
-#undef MO_TRY
-    cleanup();
-    newid.resize(n);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-    for (int64_t k = 0; k < (int64_t)n; ++k) newid[order[k]] = (int)k;
-    return cudaSuccess;
-}
-
 static void destroy_ctx(swe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -396,6 +342,17 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
         if (bad == 5) return fail(SWE_ERR_INVALID, "swe_create: element_edges id out of range");
         if (bad == 6) return fail(SWE_ERR_INVALID, "swe_create: element_neighbours id out of range / unsupported boundary");
     }
+    // SWE_B200_TIMING=1: phase times of the set-up on stderr
+    const bool timing = std::getenv("SWE_B200_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[swe_create] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
+    lap("validate");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -420,50 +377,93 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
         for (int64_t t = 0; t < nt; ++t)
             if (cell_class[t] > 3) { delete c; return fail(SWE_ERR_INVALID, "swe_create_classes: class ids must be 0..3"); }
 
-    // ---- numbering: caller id -> device id ----
-    std::vector<int> cell_new, edge_new, node_new;
-    try {
-        if (c->reordered) {
-            double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    // ---- upload the caller's arrays as they are; numbering, conversion and checks run on the device ----
+#define CREATE_TRY(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            std::string msg_ = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            free_setup();                                                                         \
+            destroy_ctx(c);                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? SWE_ERR_NOMEM : SWE_ERR_CUDA, msg_);    \
+        }                                                                                         \
+    } while (0)
+    long long *d_tp64 = nullptr, *d_te64 = nullptr, *d_tt64 = nullptr, *d_ep64 = nullptr, *d_et64 = nullptr;
+    double *d_geom = nullptr;
+    unsigned char *d_cls = nullptr;
+    int *d_cell_new = nullptr, *d_edge_new = nullptr, *d_node_new = nullptr;  // caller id -> device id (nullptr: identity)
+    int *d_ep0 = nullptr, *d_bad = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    int *d_vals = nullptr;
+    void *d_tmp = nullptr;
+    auto free_setup = [&]() {
+        void *ptrs[] = {d_tp64, d_te64, d_tt64, d_ep64, d_et64, d_geom, d_cls, d_cell_new, d_edge_new, d_node_new, d_ep0, d_bad,
+                        d_keys, d_keys2, d_vals, d_tmp};
+        for (void *q : ptrs) if (q) cudaFree(q);
+    };
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 incidence arrays");
+    CREATE_TRY(dalloc(&d_tp64, (size_t)3 * nt)); CREATE_TRY(dalloc(&d_te64, (size_t)3 * nt)); CREATE_TRY(dalloc(&d_tt64, (size_t)3 * nt));
+    CREATE_TRY(dalloc(&d_ep64, (size_t)2 * ne)); CREATE_TRY(dalloc(&d_et64, (size_t)2 * ne)); CREATE_TRY(dalloc(&d_geom, (size_t)3 * nn));
+    CREATE_TRY(cudaMemcpy(d_tp64, mesh->element_nodes, sizeof(int64_t) * 3 * nt, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(d_te64, mesh->element_edges, sizeof(int64_t) * 3 * nt, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(d_tt64, mesh->element_neighbours, sizeof(int64_t) * 3 * nt, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(d_ep64, mesh->edge_nodes, sizeof(int64_t) * 2 * ne, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(d_et64, mesh->edge_elements, sizeof(int64_t) * 2 * ne, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(d_geom, mesh->geometry, sizeof(double) * 3 * nn, cudaMemcpyHostToDevice));
+    lap("upload caller arrays");
+
+    // ---- numbering: caller id -> device id (space-filling-curve order, stable CUB radix sort of the keys) ----
+    if (c->reordered) {
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(min : x0, y0) reduction(max : x1, y1)
-            for (int64_t p = 0; p < nn; ++p) {
-                x0 = std::min(x0, mesh->geometry[3 * p]); x1 = std::max(x1, mesh->geometry[3 * p]);
-                y0 = std::min(y0, mesh->geometry[3 * p + 1]); y1 = std::max(y1, mesh->geometry[3 * p + 1]);
-            }
-            const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
-            const double sc = 2097152.0 / span;
-            std::vector<double> xs((size_t)nt), ys((size_t)nt);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-            for (int64_t t = 0; t < nt; ++t) {
-                const int64_t *q = &mesh->element_nodes[3 * t];
-                xs[t] = (mesh->geometry[3 * q[0]] + mesh->geometry[3 * q[1]] + mesh->geometry[3 * q[2]]) / 3.;
-                ys[t] = (mesh->geometry[3 * q[0] + 1] + mesh->geometry[3 * q[1] + 1] + mesh->geometry[3 * q[2] + 1]) / 3.;
-            }
-            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, cell_new, cell_class, reorder != 0)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
-            if (reorder != 0) {
-            xs.resize((size_t)ne); ys.resize((size_t)ne);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-            for (int64_t e = 0; e < ne; ++e) {
-                const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
-                xs[e] = 0.5 * (mesh->geometry[3 * a] + mesh->geometry[3 * b]);
-                ys[e] = 0.5 * (mesh->geometry[3 * a + 1] + mesh->geometry[3 * b + 1]);
-            }
-            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, edge_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
-            xs.resize((size_t)nn); ys.resize((size_t)nn);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-            for (int64_t p = 0; p < nn; ++p) { xs[p] = mesh->geometry[3 * p]; ys[p] = mesh->geometry[3 * p + 1]; }
-            if ((ce = morton_order(xs, ys, x0, y0, sc, sc, node_new)) != cudaSuccess) { delete c; return fail(SWE_ERR_CUDA, std::string("morton sort: ") + cudaGetErrorString(ce)); }
-            } else {
-                edge_new.resize((size_t)ne); std::iota(edge_new.begin(), edge_new.end(), 0);
-                node_new.resize((size_t)nn); std::iota(node_new.begin(), node_new.end(), 0);
-            }
-        } else {
-            cell_new.resize((size_t)nt); std::iota(cell_new.begin(), cell_new.end(), 0);
-            edge_new.resize((size_t)ne); std::iota(edge_new.begin(), edge_new.end(), 0);
-            node_new.resize((size_t)nn); std::iota(node_new.begin(), node_new.end(), 0);
+        for (int64_t p = 0; p < nn; ++p) {
+            x0 = std::min(x0, mesh->geometry[3 * p]); x1 = std::max(x1, mesh->geometry[3 * p]);
+            y0 = std::min(y0, mesh->geometry[3 * p + 1]); y1 = std::max(y1, mesh->geometry[3 * p + 1]);
         }
-    } catch (const std::bad_alloc &) { delete c; return fail(SWE_ERR_NOMEM, "out of host memory"); }
-    c->cell_new = cell_new;
+        const double span = std::max(std::max(x1 - x0, y1 - y0), 1e-300);
+        const KeyBox box{x0, y0, 2097152.0 / span};
+        const size_t nmax = (size_t)std::max(std::max(nt, ne), nn);
+        CREATE_TRY(dalloc(&d_keys, nmax)); CREATE_TRY(dalloc(&d_keys2, nmax)); CREATE_TRY(dalloc(&d_vals, nmax));
+        size_t tmp_bytes = 0;
+        CREATE_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals, (int64_t)nmax, 0, 45));
+        CREATE_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 1)));
+        if (cell_class) {
+            CREATE_TRY(dalloc(&d_cls, (size_t)nt));
+            CREATE_TRY(cudaMemcpy(d_cls, cell_class, (size_t)nt, cudaMemcpyHostToDevice));
+        }
+        // order[k] = caller id of device id k (= the *_old maps kept by the context); newid = its inverse
+        auto number = [&](int which, int64_t n, const long long *ids, const unsigned char *cls, int **old_out, int **new_out) -> cudaError_t {
+            cudaError_t e;
+            k_order_keys<<<nblk(n, 256), 256>>>(which, (long long)n, ids, d_geom, box, cls, reorder != 0 ? 1 : 0, d_keys, d_vals);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = dalloc(old_out, (size_t)n)) != cudaSuccess) return e;
+            if ((e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, *old_out, n, 0, 45)) != cudaSuccess) return e;
+            if ((e = dalloc(new_out, (size_t)n)) != cudaSuccess) return e;
+            k_invert_perm<<<nblk(n, 256), 256>>>((int)n, *old_out, *new_out);
+            return cudaGetLastError();
+        };
+        CREATE_TRY(number(0, nt, d_tp64, d_cls, &c->cell_old, &d_cell_new));
+        if (reorder != 0) {
+            CREATE_TRY(number(1, ne, d_ep64, nullptr, &c->edge_old, &d_edge_new));
+            CREATE_TRY(number(2, nn, nullptr, nullptr, &c->node_old, &d_node_new));
+        } else {  // classes only: edges and nodes keep the caller's numbering (identity maps, as before)
+            std::vector<int> id((size_t)std::max(ne, nn));
+            std::iota(id.begin(), id.end(), 0);
+            CREATE_TRY(dalloc(&c->edge_old, (size_t)ne)); CREATE_TRY(dalloc(&c->node_old, (size_t)nn));
+            CREATE_TRY(cudaMemcpy(c->edge_old, id.data(), sizeof(int) * ne, cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMemcpy(c->node_old, id.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
+        }
+        try {
+            c->cell_new.resize((size_t)nt);
+        } catch (const std::bad_alloc &) { free_setup(); destroy_ctx(c); return fail(SWE_ERR_NOMEM, "out of host memory"); }
+        CREATE_TRY(cudaMemcpy(c->cell_new.data(), d_cell_new, sizeof(int) * nt, cudaMemcpyDeviceToHost));
+    } else {
+        try {
+            c->cell_new.resize((size_t)nt);
+        } catch (const std::bad_alloc &) { free_setup(); destroy_ctx(c); return fail(SWE_ERR_NOMEM, "out of host memory"); }
+        std::iota(c->cell_new.begin(), c->cell_new.end(), 0);
+    }
+    lap("numbering (keys + sorts)");
     {   // device range of every ordering class (one class = everything when none are given)
         int counts[5] = {0, 0, 0, 0, 0};
         if (cell_class) for (int64_t t = 0; t < nt; ++t) counts[cell_class[t]]++; else counts[0] = (int)nt;
@@ -471,51 +471,27 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
         for (int q = 0; q < 5; ++q) c->class_first[q + 1] = c->class_first[q] + counts[q];
     }
 
-#define CREATE_TRY(call)                                                                          \
-    do {                                                                                          \
-        cudaError_t e_ = (call);                                                                  \
-        if (e_ != cudaSuccess) {                                                                  \
-            std::string msg_ = std::string(#call) + ": " + cudaGetErrorString(e_);                \
-            destroy_ctx(c);                                                                       \
-            return fail(e_ == cudaErrorMemoryAllocation ? SWE_ERR_NOMEM : SWE_ERR_CUDA, msg_);    \
-        }                                                                                         \
-    } while (0)
-
-    // ---- host-side conversion to int32 SoA in device numbering ----
+    // ---- conversion to int32 SoA in device numbering + the checks of the local convention the kernels rely on
+    // (SURVEY App. B rules 3-4, notebooks/topology.dat): TriangEdges[k] joins TriangPoints[k] and TriangPoints[(k+1)%3],
+    // TriangTriangs[k] lies across it ----
     {
-        std::vector<int> h_tp((size_t)3 * nt), h_tt((size_t)3 * nt), h_te((size_t)3 * nt);
+        CREATE_TRY(dalloc(&c->tp, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->tt, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->te, (size_t)3 * nt));
+        CREATE_TRY(dalloc(&d_bad, 1));
+        CREATE_TRY(cudaMemset(d_bad, 0, sizeof(int)));
+        k_convert_cells<<<nblk(nt, 256), 256>>>((int)nt, d_tp64, d_te64, d_tt64, d_ep64, d_et64, d_cell_new, d_edge_new, d_node_new, c->tp,
+                                               c->tt, c->te, d_bad);
+        CREATE_TRY(cudaGetLastError());
         int inconsistent = 0;
-#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(max : inconsistent)
-        for (int64_t t = 0; t < nt; ++t) {
-            const int d = cell_new[t];
-            for (int k = 0; k < 3; ++k) {
-                h_tp[(size_t)k * nt + d] = node_new[mesh->element_nodes[3 * t + k]];
-                const int64_t nb = mesh->element_neighbours[3 * t + k];
-                h_tt[(size_t)k * nt + d] = nb >= 0 ? cell_new[nb] : (int)nb;
-                const int64_t e = mesh->element_edges[3 * t + k];
-                const bool first = mesh->edge_elements[2 * e] == t;
-                if (!first && mesh->edge_elements[2 * e + 1] != t) inconsistent = std::max(inconsistent, 1);
-                // local convention the kernels rely on (SURVEY App. B rules 3-4, notebooks/topology.dat):
-                // TriangEdges[k] joins TriangPoints[k] and TriangPoints[(k+1)%3], TriangTriangs[k] lies across it
-                const int64_t a = mesh->edge_nodes[2 * e], b = mesh->edge_nodes[2 * e + 1];
-                const int64_t p = mesh->element_nodes[3 * t + k], q = mesh->element_nodes[3 * t + (k + 1) % 3];
-                if (!((a == p && b == q) || (a == q && b == p))) inconsistent = std::max(inconsistent, 2);
-                const int64_t across = first ? mesh->edge_elements[2 * e + 1] : mesh->edge_elements[2 * e];
-                if (across != nb) inconsistent = std::max(inconsistent, 3);
-                h_te[(size_t)k * nt + d] = first ? edge_new[e] : ~edge_new[e];
-            }
-        }
+        CREATE_TRY(cudaMemcpy(&inconsistent, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
         if (inconsistent) {
+            free_setup();
             destroy_ctx(c);
             return fail(SWE_ERR_INVALID,
                         inconsistent == 1 ? "swe_create: element_edges / edge_elements are inconsistent"
                         : inconsistent == 2 ? "swe_create: element_edges[k] must join element_nodes[k] and element_nodes[(k+1)%3]"
                                             : "swe_create: element_neighbours[k] must be the cell across element_edges[k]");
         }
-        CREATE_TRY(dalloc(&c->tp, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->tt, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->te, (size_t)3 * nt));
-        CREATE_TRY(cudaMemcpy(c->tp, h_tp.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(c->tt, h_tt.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(c->te, h_te.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice));
+        lap("cell incidence -> int32 SoA");
         // node -> incident cells (CSR, device numbering; pass 2 gathers the node maxima over it), built on the device:
         // histogram of the node ids -> exclusive scan = row starts; stable sort of (node, cell) pairs = row contents
         {
@@ -537,47 +513,23 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
             cudaFree(tmp); cudaFree(keys_out); cudaFree(vals_in);
         }
     }
-    int *d_ep0 = nullptr, *d_ep1 = nullptr, *d_et0 = nullptr, *d_et1 = nullptr;
-    {
-        std::vector<int> h((size_t)4 * ne);
-        int *ep0 = h.data(), *ep1 = ep0 + ne, *et0 = ep1 + ne, *et1 = et0 + ne;
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-        for (int64_t e = 0; e < ne; ++e) {
-            const int d = edge_new[e];
-            ep0[d] = node_new[mesh->edge_nodes[2 * e]]; ep1[d] = node_new[mesh->edge_nodes[2 * e + 1]];
-            et0[d] = cell_new[mesh->edge_elements[2 * e]];
-            const int64_t b = mesh->edge_elements[2 * e + 1];
-            et1[d] = b >= 0 ? cell_new[b] : (int)b;
-        }
-        CREATE_TRY(dalloc(&d_ep0, (size_t)4 * ne));
-        d_ep1 = d_ep0 + ne; d_et0 = d_ep1 + ne; d_et1 = d_et0 + ne;
-        CREATE_TRY(cudaMemcpy(d_ep0, h.data(), sizeof(int) * 4 * ne, cudaMemcpyHostToDevice));
-    }
-    {
-        std::vector<double> h((size_t)4 * nn);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-        for (int64_t p = 0; p < nn; ++p) {
-            double *q = &h[(size_t)4 * node_new[p]];
-            q[0] = mesh->geometry[3 * p]; q[1] = mesh->geometry[3 * p + 1]; q[2] = mesh->geometry[3 * p + 2]; q[3] = 0.;
-        }
-        CREATE_TRY(dalloc(&c->node, (size_t)nn));
-        CREATE_TRY(cudaMemcpy(c->node, h.data(), sizeof(double) * 4 * nn, cudaMemcpyHostToDevice));
-    }
-    if (c->reordered) {
-        std::vector<int> inv((size_t)std::max(std::max(nt, ne), nn));
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-        for (int64_t t = 0; t < nt; ++t) inv[cell_new[t]] = (int)t;
-        CREATE_TRY(dalloc(&c->cell_old, (size_t)nt));
-        CREATE_TRY(cudaMemcpy(c->cell_old, inv.data(), sizeof(int) * nt, cudaMemcpyHostToDevice));
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-        for (int64_t e = 0; e < ne; ++e) inv[edge_new[e]] = (int)e;
-        CREATE_TRY(dalloc(&c->edge_old, (size_t)ne));
-        CREATE_TRY(cudaMemcpy(c->edge_old, inv.data(), sizeof(int) * ne, cudaMemcpyHostToDevice));
-#pragma omp parallel for schedule(static) num_threads(host_threads())
-        for (int64_t p = 0; p < nn; ++p) inv[node_new[p]] = (int)p;
-        CREATE_TRY(dalloc(&c->node_old, (size_t)nn));
-        CREATE_TRY(cudaMemcpy(c->node_old, inv.data(), sizeof(int) * nn, cudaMemcpyHostToDevice));
-    }
+    lap("node->cell CSR");
+    int *d_ep1 = nullptr, *d_et0 = nullptr, *d_et1 = nullptr;
+    CREATE_TRY(dalloc(&d_ep0, (size_t)4 * ne));
+    d_ep1 = d_ep0 + ne; d_et0 = d_ep1 + ne; d_et1 = d_et0 + ne;
+    k_convert_edges<<<nblk(ne, 256), 256>>>((int)ne, d_ep64, d_et64, d_cell_new, d_edge_new, d_node_new, d_ep0, d_ep1, d_et0, d_et1);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(dalloc(&c->node, (size_t)nn));
+    k_convert_nodes<<<nblk(nn, 256), 256>>>((int)nn, d_geom, d_node_new, c->node);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaDeviceSynchronize());
+    // the int64 copies and the forward maps are no longer needed
+    cudaFree(d_tp64); cudaFree(d_te64); cudaFree(d_tt64); cudaFree(d_ep64); cudaFree(d_et64); cudaFree(d_geom); cudaFree(d_cls);
+    cudaFree(d_cell_new); cudaFree(d_edge_new); cudaFree(d_node_new); cudaFree(d_bad); cudaFree(d_keys); cudaFree(d_keys2);
+    cudaFree(d_vals); cudaFree(d_tmp);
+    d_tp64 = d_te64 = d_tt64 = d_ep64 = d_et64 = nullptr; d_geom = nullptr; d_cls = nullptr;
+    d_cell_new = d_edge_new = d_node_new = d_bad = nullptr; d_keys = d_keys2 = nullptr; d_vals = nullptr; d_tmp = nullptr;
+    lap("edges, nodes, inverse maps");
     // ---- geometry on device ----
     CREATE_TRY(dalloc(&c->cgeo, (size_t)nt)); CREATE_TRY(dalloc(&c->area, (size_t)nt)); CREATE_TRY(dalloc(&c->cb, (size_t)nt));
     CREATE_TRY(dalloc(&c->slotL, (size_t)ne)); CREATE_TRY(dalloc(&c->slotR, (size_t)ne));
@@ -591,7 +543,9 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(cudaGetLastError());
     CREATE_TRY(cudaDeviceSynchronize());
     cudaFree(d_ep0);
+    d_ep0 = nullptr;
     c->launches += 3;
+    lap("geometry kernels");
     // ---- fields ----
     for (int q = 0; q < 3; ++q) { CREATE_TRY(dalloc(&c->bufA[q], (size_t)nt)); CREATE_TRY(dalloc(&c->bufB[q], (size_t)nt)); }
     c->cur = c->bufA; c->sav = c->bufA;
@@ -636,6 +590,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
         c->launches += 1;
     }
 #undef CREATE_TRY
+    lap("fields + drain list");
     *out = c;
     return SWE_OK;
 }

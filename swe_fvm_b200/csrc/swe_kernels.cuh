@@ -753,7 +753,7 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 #ifndef SWE_K2_GRID_PER_SM
-#define SWE_K2_GRID_PER_SM 16
+#define SWE_K2_GRID_PER_SM 64  // A/B at 64M cells: 16 -> 2.114 ms, 64 -> 2.062 ms, one block per 128 edges -> 2.889 ms
 #endif
 #ifndef SWE_K2_MIN_BLOCKS
 #define SWE_K2_MIN_BLOCKS 8
@@ -1056,6 +1056,107 @@ __global__ void k_setup_cells(int nt, const int *tp, const int *tt, const double
     cb[i] = g.z;
     const double ax = P1.x - P0.x, ay = P1.y - P0.y, bx = P2.x - P0.x, by = P2.y - P0.y;
     area[i] = 0.5 * fabs(ax * by - bx * ay);  // Domain::Area (:87-90)
+}
+
+// ---------------------------------------------------------------------------------------
+// set-up on the device: the caller's int64 incidence arrays and 3 x nn geometry are uploaded as they are; the
+// locality-preserving numbering (Hilbert keys + CUB sort), the conversion to int32 structure-of-arrays in device
+// numbering and the consistency checks of the local edge order run as kernels (at 64M cells the host loops that did
+// this before cost 6.5 of the 10 s of set-up).
+// ---------------------------------------------------------------------------------------
+// Hilbert-curve index of a point on the 2^21 x 2^21 grid (no quadrant jumps, unlike the Z-order / Morton curve)
+__host__ __device__ inline unsigned long long hilbert21(unsigned long long x, unsigned long long y) {
+    const unsigned long long n = 1ull << 21;
+    unsigned long long d = 0;
+    for (unsigned long long s = n >> 1; s > 0; s >>= 1) {
+        const unsigned long long rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        d += s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = n - 1 - x; y = n - 1 - y; }
+            const unsigned long long t = x; x = y; y = t;
+        }
+    }
+    return d;
+}
+struct KeyBox { double x0, y0, scale; };
+__device__ __forceinline__ unsigned long long curve_key(double x, double y, const KeyBox &b) {
+    const unsigned long long qx = (unsigned long long)fmin(2097151.0, fmax(0.0, (x - b.x0) * b.scale));
+    const unsigned long long qy = (unsigned long long)fmin(2097151.0, fmax(0.0, (y - b.y0) * b.scale));
+    return hilbert21(qx, qy);
+}
+// which: 0 cells (centroid; ids = element_nodes, 3 per row), 1 edges (midpoint; ids = edge_nodes, 2 per row), 2 nodes.
+// curve == 0 keeps the caller's order (inside every class); cls (cells only): class id in the bits above the curve key.
+__global__ void k_order_keys(int which, long long n, const long long *ids, const double *geom, KeyBox box, const unsigned char *cls,
+                             int curve, unsigned long long *keys, int *vals) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = (unsigned long long)i;
+    if (curve) {
+        double x, y;
+        if (which == 0) {
+            const long long a = ids[3 * i], b = ids[3 * i + 1], c = ids[3 * i + 2];
+            x = (geom[3 * a] + geom[3 * b] + geom[3 * c]) / 3.;
+            y = (geom[3 * a + 1] + geom[3 * b + 1] + geom[3 * c + 1]) / 3.;
+        } else if (which == 1) {
+            const long long a = ids[2 * i], b = ids[2 * i + 1];
+            x = 0.5 * (geom[3 * a] + geom[3 * b]);
+            y = 0.5 * (geom[3 * a + 1] + geom[3 * b + 1]);
+        } else {
+            x = geom[3 * i]; y = geom[3 * i + 1];
+        }
+        key = curve_key(x, y, box);
+    }
+    if (cls) key |= (unsigned long long)cls[i] << 42;
+    keys[i] = key;
+    vals[i] = (int)i;
+}
+__global__ void k_invert_perm(int n, const int *order, int *newid) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) newid[order[k]] = k;
+}
+// maps: caller id -> device id, nullptr = identity
+__device__ __forceinline__ int map_id(const int *map, long long i) { return map ? map[i] : (int)i; }
+// cell incidence -> k-major int32 SoA in device numbering; bad[0] = max code of a violated local convention
+// (1 element_edges / edge_elements inconsistent, 2 edge k does not join nodes k, k+1, 3 neighbour k is not across edge k)
+__global__ void k_convert_cells(int nt, const long long *tp64, const long long *te64, const long long *tt64, const long long *ep64,
+                                const long long *et64, const int *cell_new, const int *edge_new, const int *node_new, int *tp,
+                                int *tt, int *te, int *bad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const int d = map_id(cell_new, t);
+    int worst = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        tp[(size_t)k * nt + d] = map_id(node_new, tp64[3 * (size_t)t + k]);
+        const long long nb = tt64[3 * (size_t)t + k];
+        tt[(size_t)k * nt + d] = nb >= 0 ? map_id(cell_new, nb) : (int)nb;
+        const long long e = te64[3 * (size_t)t + k];
+        const bool first = et64[2 * e] == t;
+        if (!first && et64[2 * e + 1] != t) worst = max(worst, 1);
+        const long long a = ep64[2 * e], b = ep64[2 * e + 1];
+        const long long p = tp64[3 * (size_t)t + k], q = tp64[3 * (size_t)t + (k + 1) % 3];
+        if (!((a == p && b == q) || (a == q && b == p))) worst = max(worst, 2);
+        const long long across = first ? et64[2 * e + 1] : et64[2 * e];
+        if (across != nb) worst = max(worst, 3);
+        const int en = map_id(edge_new, e);
+        te[(size_t)k * nt + d] = first ? en : ~en;
+    }
+    if (worst) atomicMax(bad, worst);
+}
+__global__ void k_convert_edges(int ne, const long long *ep64, const long long *et64, const int *cell_new, const int *edge_new,
+                                const int *node_new, int *ep0, int *ep1, int *et0, int *et1) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const int d = map_id(edge_new, e);
+    ep0[d] = map_id(node_new, ep64[2 * (size_t)e]); ep1[d] = map_id(node_new, ep64[2 * (size_t)e + 1]);
+    et0[d] = map_id(cell_new, et64[2 * (size_t)e]);
+    const long long b = et64[2 * (size_t)e + 1];
+    et1[d] = b >= 0 ? map_id(cell_new, b) : (int)b;
+}
+__global__ void k_convert_nodes(int nn, const double *geom, const int *node_new, double4 *node) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nn) return;
+    node[map_id(node_new, p)] = make_double4(geom[3 * (size_t)p], geom[3 * (size_t)p + 1], geom[3 * (size_t)p + 2], 0.);
 }
 
 // node -> cells CSR set-up: count the incident cells of every node and emit the cell id of each (corner, cell) pair
