@@ -43,7 +43,8 @@ B_PER_CELL_UPDATE_SSPRK2 = 1488.0  # 744 B per cell-stage x 2 
 KERNEL_BYTES_PER_CELL = {
     "k_reconstruct": 185.0,  # W 24 + tt,tp 24 + cgeo 32 + nodes 16 | ceh,ceu,cev 72 + cgx,cgy 16 + cls 1
     "k_partwet2": 0.0,       # work list only (O(sqrt N) part-wet cells)
-    "k_flux": 156.0,         # per edge: slots 8 + n 16 + dmin 8 + two sides 48 | F 24; x 1.5 edges per cell
+    "k_flux": 150.0,         # per edge: slots 8 + n 16 + two sides 48 (+ dmin 8 on the LAST stage only: the CFL minimum of
+                             # the earlier stages is a dead value) | F 24; x 1.5 edges per cell -> 144 (stage 1) / 156 (stage 2), mean 150
     "k_drain": 56.0,         # te 12 + F0 12 + w 8 + cb 8 + area 8 | dti 8
     "k_halo_pack_signal": 0.0, "k_halo_wait_unpack": 0.0, "k_min_push_pull": 0.0,  # O(sqrt N) halo / scalar kernels (N > 1)
     "k_update": 220.0,       # W 24 + (U0 24 on the 2nd stage) + te,tt 24 + F 36 + dti 8 + ceh 24 + grad 16 + n 24 +
@@ -52,7 +53,7 @@ KERNEL_BYTES_PER_CELL = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# profiles/r1_v3_ncu_full_summary.csv (64M-cell fully-wet workload); None for other workloads
+# profiles/r2_ncu_full_summary.csv (64M-cell fully-wet workload); None for other workloads
 NCU_TRAFFIC_BYTES_64M = {"k_reconstruct": 12.752e9, "k_flux": 10.571e9, "k_drain": 3.751e9, "k_update": 13.980e9}
 
 
@@ -272,7 +273,18 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the communicator is created (NCCL_DEBUG=VERSION on some boxes):
+        # keep stdout for the one JSON line, send everything else to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     if rank == 0:
         import __graft_entry__ as g
         g.build()

@@ -6,7 +6,7 @@
 
 #include "TriangMesh.h"
 
-constexpr inline bool IsWet(double h) noexcept { return h > 1e-12; }  // upstream include/Bathymetry.h:5-8
+constexpr inline bool IsWet(double h) noexcept { return h > SWE_WET_DEPTH; }  // upstream include/Bathymetry.h:5-8
 inline Point DryState(double b) noexcept { return {b, 0., 0.}; }
 
 struct Domain {

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../swe_b200.h"
+#include "../swe_constants.h"
 
 using Idx = int64_t;  // upstream: Eigen::Index (include/Includes.h:18)
 
@@ -41,4 +42,4 @@ struct Storage {
     void set_col(size_t c, const Array<k> &a) { for (size_t r = 0; r < k; ++r) data[k * c + r] = a[r]; }
 };
 
-constexpr inline double tol = 1e-13;  // upstream include/Includes.h:30
+constexpr inline double tol = SWE_TOL;  // upstream include/Includes.h:30

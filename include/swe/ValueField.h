@@ -14,7 +14,7 @@ struct PrimAssigner {  // upstream src/Assigners.cpp:4-20
         const double h = rhs[0] - b;
         if (!IsWet(h)) { f->set_col(col, DryState(b)); return; }
         Array<3> v = rhs;
-        if (h < 1e-3) { const double s = std::sqrt(2) * h / std::sqrt(h * h + 1e-6); v[1] *= s; v[2] *= s; }
+        if (h < SWE_DAMP_DEPTH) { const double s = std::sqrt(2) * h / std::sqrt(h * h + SWE_DAMP_EPS_PRIM); v[1] *= s; v[2] *= s; }
         f->set_col(col, v);
     }
 };
@@ -24,7 +24,7 @@ struct ConsAssigner {  // upstream src/Assigners.cpp:22-44
     void operator=(const Array<3> &rhs) {
         const double h = rhs[0];
         if (!IsWet(h)) { f->set_col(col, DryState(b)); return; }
-        const double ih = (h < 1e-3) ? std::sqrt(2) * h / std::sqrt(h * h * h * h + 1e-12) : 1. / h;
+        const double ih = (h < SWE_DAMP_DEPTH) ? std::sqrt(2) * h / std::sqrt(h * h * h * h + SWE_DAMP_EPS_CONS) : 1. / h;
         f->set_col(col, {h + b, rhs[1] * ih, rhs[2] * ih});
     }
     void operator+=(const Array<3> &rhs) { *this = Get() + rhs; }

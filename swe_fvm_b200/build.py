@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libswe_b200.so")
 SOURCES = ["swe_b200.cu", "hostmesh.cpp", "distplan.cpp"]
-HEADERS = ["swe_kernels.cuh", "swe_device.cuh", "swe_cases.cuh", "swe_dist.cuh", "swe_flux_registry.cuh", "user_fluxes.cuh", "hostmesh.hpp", "distplan.hpp", os.path.join("..", "..", "include", "swe_b200.h")]
+HEADERS = ["swe_kernels.cuh", "swe_device.cuh", "swe_cases.cuh", "swe_dist.cuh", "swe_flux_registry.cuh", "user_fluxes.cuh", "hostmesh.hpp", "distplan.hpp", os.path.join("..", "..", "include", "swe_b200.h"), os.path.join("..", "..", "include", "swe_constants.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

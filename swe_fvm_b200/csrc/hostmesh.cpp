@@ -11,6 +11,7 @@
 //   5. EdgeTriangs = (later-visiting triangle, earlier-visiting triangle), walls (owner,-1).
 // Plus what the multi-GPU path needs: 1->4 refinement, RCB partition, sub-mesh extraction.
 #include "hostmesh.hpp"
+#include "../../include/swe_constants.h"
 
 #include <algorithm>
 #include <cmath>
@@ -567,10 +568,10 @@ void case_initial_state(const swe_case &c, const swe_hostmesh &m, int quad_n, do
         // PrimAssigner::operator= (src/Assigners.cpp:8-20)
         double h = x[0] - bi;
         double *o = &prim[3 * i];
-        if (!(h > 1e-12)) { o[0] = bi; o[1] = 0.; o[2] = 0.; continue; }
+        if (!(h > SWE_WET_DEPTH)) { o[0] = bi; o[1] = 0.; o[2] = 0.; continue; }
         o[0] = x[0]; o[1] = x[1]; o[2] = x[2];
-        if (h < 1e-3) {
-            double f = std::sqrt(2) * h / std::sqrt(h * h + 1e-6);
+        if (h < SWE_DAMP_DEPTH) {
+            double f = std::sqrt(2) * h / std::sqrt(h * h + SWE_DAMP_EPS_PRIM);
             o[1] *= f; o[2] *= f;
         }
     }

@@ -48,6 +48,7 @@ struct swe_ctx {
     // sit on a 128-cell tile border, so the list pass costs 0.62 ms against 0.73 ms for the full pass, and the fused
     // update needs 104 registers + a barrier (2.75 vs 2.23 ms)
     int opt_fused_drain = 0;
+    int opt_skip_cfl = 1;  // non-final stages of a step run the flux kernel without the CFL minimum (a dead value upstream too)
     int *drain_list = nullptr;
     int drain_count = 0;
     bool dti_complete = false;  // c->dti holds the draining dt of EVERY cell (full k_drain ran for the last stage)
@@ -234,7 +235,7 @@ static bool fluxer_known(int id) {
     for (int k = 0; k < kNumFluxers; ++k) if (g_fluxers[k].id == id) return true;
     return false;
 }
-static void launch_flux(swe_ctx *c, const DevMesh &m, const DevFields &s, int fluxer_id) {
+static void launch_flux(swe_ctx *c, const DevMesh &m, const DevFields &s, int fluxer_id, bool cfl = true) {
     const int g = std::min(nblk(c->ne, kBlock), c->sms * SWE_K2_GRID_PER_SM);
     const double ac = std::fabs(c->cor);
     const int rf = c->opt_roe_fix, ca = c->opt_cfl_abs;
@@ -242,7 +243,10 @@ static void launch_flux(swe_ctx *c, const DevMesh &m, const DevFields &s, int fl
     switch (fluxer_id) {
 #define SWE_X(ID, NAME, TYPE)                                                            \
         case ID:                                                                         \
-            if (opt) k_flux<TYPE, true><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);   \
+            if (!cfl) {                                                                  \
+                if (opt) k_flux<TYPE, true, false><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);  \
+                else k_flux<TYPE, false, false><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);     \
+            } else if (opt) k_flux<TYPE, true><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);       \
             else k_flux<TYPE, false><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);      \
             break;
         SWE_FLUX_LIST(SWE_X)
@@ -266,7 +270,8 @@ static void preload_kernels() {
     SWE_LOAD(k_reconstruct_pf<T, 0>); SWE_LOAD(k_reconstruct_pf<T, 1>); SWE_LOAD(k_reconstruct_pf<T, 2>); \
     SWE_LOAD(k_reconstruct_slow<T>); SWE_LOAD(k_partwet2<T>)
     SWE_LOAD_K1(false); SWE_LOAD_K1(true);
-#define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>);
+#define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>); \
+    SWE_LOAD(k_flux<TYPE, false, false>); SWE_LOAD(k_flux<TYPE, true, false>);
     SWE_FLUX_LIST(SWE_X)
 #undef SWE_X
     SWE_LOAD(k_drain); SWE_LOAD(k_drain_list);
@@ -764,7 +769,8 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "graph")) { if (value < -1 || value > 1) return bad("-1 auto, 0 off, 1 on"); c->opt_graph = value; }
     else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > 2 * SWE_K1_TILED) return bad("0 gather kernel, 1 TMA-staged shared-memory tiles, 2 cp.async software pipeline"); c->opt_tiled = value; }
     else if (!std::strcmp(key, "fused_drain")) { if (value < 0 || value > 1) return bad("0 separate k_drain pass, 1 draining dt fused into the stage update"); c->opt_fused_drain = value; }
-    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, graph)");
+    else if (!std::strcmp(key, "skip_cfl")) { if (value < 0 || value > 1) return bad("0 every stage rebuilds the CFL minimum, 1 only the last stage of a step"); c->opt_skip_cfl = value; }
+    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, skip_cfl, graph)");
     return SWE_OK;
 }
 SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
@@ -775,6 +781,7 @@ SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
     else if (!std::strcmp(key, "cfl_abs")) *value = c->opt_cfl_abs;
     else if (!std::strcmp(key, "k1_tiled")) *value = c->opt_tiled;
     else if (!std::strcmp(key, "fused_drain")) *value = c->opt_fused_drain;
+    else if (!std::strcmp(key, "skip_cfl")) *value = c->opt_skip_cfl;
     else if (!std::strcmp(key, "graph")) *value = c->opt_graph;
     else { c->err = std::string("swe_get_option: unknown option ") + key; return SWE_ERR_INVALID; }
     return SWE_OK;
@@ -872,7 +879,10 @@ SWE_API int swe_compute_interface_values_range(swe_ctx *c, int64_t first_cell, i
     return interface_values_range(c, (int)first_cell, (int)last_cell, begin != 0, finish != 0);
 }
 
-SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {
+// cfl = false (internal, non-final stages of a step): fluxes only, min_length_to_wavespeed is left alone
+static int compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws, bool cfl);
+SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) { return compute_fluxes(c, flux, ws, true); }
+static int compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws, bool cfl) {
     if (!c) return SWE_ERR_INVALID;
     int id = c->fluxer;  // swe_set_fluxer overrides the enum pair
     if (id < 0) {
@@ -886,7 +896,7 @@ SWE_API int swe_compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws) {
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     const int kt = kt_begin(c, KT_FLUX);
-    launch_flux(c, m, s, id);
+    launch_flux(c, m, s, id, cfl || c->taps || !c->opt_skip_cfl);
     kt_end(c, kt);
     return launch_check(c, "k_flux");
 }
@@ -990,13 +1000,13 @@ static int one_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed 
         return dev_dt ? stage_update(c, a0, a1, 0., coef) : stage_update(c, a0, a1, coef * dt, 0.);
     };
     if ((rc = swe_compute_interface_values(c))) return rc;
-    if ((rc = swe_compute_fluxes(c, flux, ws))) return rc;
+    if ((rc = compute_fluxes(c, flux, ws, scheme == SWE_EULER))) return rc;  // the CFL minimum of the LAST stage is the step's
     if (scheme == SWE_EULER) return dev_dt ? stage_update(c, 0., 1., 0., 1.) : stage_update(c, 0., 1., dt, 0.);
     swe_save_state(c);
     // first stage: U0 + RHS(dt)
     if ((rc = (dev_dt ? stage_update(c, 0., 1., 0., 1.) : stage_update(c, 0., 1., dt, 0.)))) return rc;
     if ((rc = swe_compute_interface_values(c))) return rc;
-    if ((rc = swe_compute_fluxes(c, flux, ws))) return rc;
+    if ((rc = compute_fluxes(c, flux, ws, scheme == SWE_SSPRK2))) return rc;
     if (scheme == SWE_SSPRK2) return upd(0.5, 0.5, 0.5);
     if ((rc = upd(0.75, 0.25, 0.25))) return rc;
     if ((rc = swe_compute_interface_values(c))) return rc;
@@ -1038,7 +1048,7 @@ static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespe
         return code;
     };
     const int fluxer = c->fluxer >= 0 ? c->fluxer : 3 * (int)flux + (int)ws;
-    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7);
+    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7) | (c->opt_skip_cfl << 10);
     for (int64_t s = 0; s < nsteps; ++s) {
         const int parity = (c->cur == c->bufA) ? 0 : 1;
         swe_ctx::StepGraph *g = nullptr;
@@ -1113,7 +1123,7 @@ SWE_API int swe_cfl_dt(swe_ctx *c, double *dt) {
     double v = 0;
     int rc = read_scalar(c, 0, &v);
     if (rc) return rc;
-    *dt = 0.15 * v;  // m_constCFL (include/TimeDisc.h:22)
+    *dt = SWE_CFL * v;  // m_constCFL (include/TimeDisc.h:22)
     return SWE_OK;
 }
 SWE_API int swe_get_time(swe_ctx *c, double *t) { return read_scalar(c, 2, t); }

@@ -118,8 +118,8 @@ __global__ void k_case_init(DevMesh m, swe_case c, int n, double t, double *w, d
     }
     const double h = x0 - bi;
     if (!is_wet(h)) { w[i] = bi; u[i] = 0.; v[i] = 0.; return; }
-    if (h < 1e-3) {
-        const double f = sqrt(2.0) * h / sqrt(h * h + 1e-6);
+    if (h < SWE_DAMP_DEPTH) {
+        const double f = sqrt(2.0) * h / sqrt(h * h + SWE_DAMP_EPS_PRIM);
         x1 *= f; x2 *= f;
     }
     w[i] = x0; u[i] = x1; v[i] = x2;

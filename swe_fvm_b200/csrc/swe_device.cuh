@@ -5,11 +5,13 @@
 #pragma once
 #include <cstdint>
 
+#include "../../include/swe_constants.h"
+
 namespace swe {
 
-constexpr double kTol = 1e-13;  // include/Includes.h:30
+constexpr double kTol = SWE_TOL;  // include/Includes.h:30
 
-__device__ __forceinline__ bool is_wet(double h) { return h > 1e-12; }  // include/Bathymetry.h:5-8
+__device__ __forceinline__ bool is_wet(double h) { return h > SWE_WET_DEPTH; }  // include/Bathymetry.h:5-8
 // std::min / std::max semantics (argument order matters for NaN and signed zeros)
 __device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b : a; }
 __device__ __forceinline__ double smax(double a, double b) { return (a < b) ? b : a; }
@@ -153,7 +155,7 @@ __device__ __forceinline__ void riemann_flux(double nx, double ny, double hl, do
     double ul = uxl * nx + uyl * ny;
     double ur = uxr * nx + uyr * ny;
     f0 = 0.; f1 = 0.; f2 = 0.;
-    if (hl + hr <= 1e-10) return;
+    if (hl + hr <= SWE_FLUX_DRY_SUM) return;
     double al, ar;
     wavespeeds<WS, OPT>(ul, hl, ur, hr, al, ar, roe_fix);
     const double Ul0 = hl, Ul1 = hl * uxl, Ul2 = hl * uyl;
@@ -161,7 +163,7 @@ __device__ __forceinline__ void riemann_flux(double nx, double ny, double hl, do
     if (FLUX == FLUX_HLL) {
         al = smin(0., al);
         ar = smax(0., ar);
-        if (ar - al <= 1e-10) return;
+        if (ar - al <= SWE_FLUX_DRY_SUM) return;
         l2w = dmin / (abscor + smax(-al, ar));
         double l0, l1, l2, r0, r1, r2;
         elem_flux(nx, ny, Ul0, Ul1, Ul2, l0, l1, l2);

@@ -263,7 +263,7 @@ static int dist_stage(swe_dist *d, swe_flux flux, swe_wavespeed ws, double a0, d
     const int world = d->plan->world;
     int rc;
     if ((rc = dist_interface_values(d))) return rc;
-    DIST_CTX(d, swe_compute_fluxes(c, flux, ws));
+    DIST_CTX(d, compute_fluxes(c, flux, ws, last));  // only the last stage's CFL minimum is ever read
     // dt of THIS step from the previous step's global minimum: first needed by the stage update below, so the wait
     // for the slowest rank hides behind the reconstruction + flux kernels above (must precede this step's push)
     if ((rc = dist_finish_min(d, false))) return rc;
@@ -473,7 +473,7 @@ SWE_API int swe_dist_cfl_dt(swe_dist *d, double *dt) {
     double v = 0.;  // scal[4] = global minimum on several GPUs, scal[0] on one
     DIST_TRY(d, cudaMemcpyAsync(&v, d->ctx->scal + (d->plan->world > 1 ? 4 : 0), sizeof(double), cudaMemcpyDeviceToHost, d->ctx->stream));
     DIST_TRY(d, cudaStreamSynchronize(d->ctx->stream));
-    *dt = 0.15 * v;
+    *dt = SWE_CFL * v;
     return SWE_OK;
 }
 

@@ -96,8 +96,8 @@ __device__ __forceinline__ void emit_edge(const DevFields &s, int slot, const Mu
     double ew = a0, eh = h;
     if (!is_wet(h)) {
         ew = mb; eh = 0.; eu = 0.; ev = 0.;
-    } else if (h < 1e-3) {
-        const double fac = sqrt(2.0) * h / sqrt(h * h + 1e-6);
+    } else if (h < SWE_DAMP_DEPTH) {
+        const double fac = sqrt(2.0) * h / sqrt(h * h + SWE_DAMP_EPS_PRIM);
         eu *= fac; ev *= fac;
     }
     st_once(s.ceh + slot, eh); st_once(s.ceu + slot, eu); st_once(s.cev + slot, ev);
@@ -758,7 +758,10 @@ __device__ __forceinline__ double warp_min(double v) {
 #ifndef SWE_K2_MIN_BLOCKS
 #define SWE_K2_MIN_BLOCKS 8
 #endif
-template <class FLUXER, bool OPT>
+// CFL = false: the instantiation for the non-final stages of a multi-stage step. m_min_length_to_wavespeed is reset
+// and rebuilt by EVERY ComputeFluxes (src/SpaceDisc.cpp:56) and only read after the step (CFLdt, include/TimeDisc.h:13),
+// so the minima of the earlier stages are dead values: no dmin load, no division, no reduction, no publish.
+template <class FLUXER, bool OPT, bool CFL = true>
 __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, DevFields s, double abscor, int roe_fix, int cfl_abs) {
     const int ne = m.ne;
     const int stride = gridDim.x * blockDim.x;
@@ -779,15 +782,16 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
             } else {
                 double cand = 1.0;
                 FLUXER::template eval<OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
-                                           __ldg(s.ceu + sr), __ldg(s.cev + sr), __ldg(m.dmin + e), abscor, f0, f1, f2, cand,
-                                           roe_fix, cfl_abs);
-                l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
+                                           __ldg(s.ceu + sr), __ldg(s.cev + sr), CFL ? __ldg(m.dmin + e) : 1.0, abscor, f0, f1, f2,
+                                           cand, roe_fix, cfl_abs);
+                if (CFL) l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
             }
             st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
             if (nx >= ne) break;
             e = nx; sl = nsl; sr = nsr;
         }
     }
+    if (!CFL) return;
     __shared__ double red[kBlock / 32];
     l2w = warp_min(l2w);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l2w;
@@ -1011,7 +1015,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
         ow = cb; ou = 0.; ov = 0.;
     } else {
         double ih;
-        if (U0 < 1e-3) ih = sqrt(2.0) * U0 / sqrt(U0 * U0 * U0 * U0 + 1e-12);
+        if (U0 < SWE_DAMP_DEPTH) ih = sqrt(2.0) * U0 / sqrt(U0 * U0 * U0 * U0 + SWE_DAMP_EPS_CONS);
         else ih = 1. / U0;
         ow = U0 + cb; ou = U1 * ih; ov = U2 * ih;
     }
@@ -1034,7 +1038,7 @@ __global__ void k_classify(DevMesh m, const double *w, signed char *cls) {
 __global__ void k_post_step(DevFields s, double dt_host, int adaptive, int min_slot) {
     const double used = adaptive ? s.scal[1] : dt_host;
     s.scal[2] += used;
-    if (adaptive) s.scal[1] = 0.15 * s.scal[min_slot];
+    if (adaptive) s.scal[1] = SWE_CFL * s.scal[min_slot];
 }
 __global__ void k_set_scalar(double *p, double v) { *p = v; }
 
