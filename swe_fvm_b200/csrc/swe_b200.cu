@@ -67,7 +67,7 @@ struct swe_ctx {
     double *bufA[3] = {nullptr, nullptr, nullptr}, *bufB[3] = {nullptr, nullptr, nullptr};
     double **cur = nullptr, **sav = nullptr;  // point at bufA / bufB
     double *ceh = nullptr, *ceu = nullptr, *cev = nullptr, *cgx = nullptr, *cgy = nullptr, *cew = nullptr;
-    double *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *dti = nullptr;
+    double *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *dti = nullptr, *pwl = nullptr;
     signed char *cls = nullptr;
     int *pw_list = nullptr, *rs_list = nullptr;
     double *scal = nullptr;
@@ -161,7 +161,7 @@ static DevFields dev_fields(const swe_ctx *c) {
     DevFields s;
     s.w = c->cur[0]; s.u = c->cur[1]; s.v = c->cur[2];
     s.ceh = c->ceh; s.ceu = c->ceu; s.cev = c->cev; s.cgx = c->cgx; s.cgy = c->cgy; s.cew = c->cew;
-    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.cls = c->cls; s.pw_list = c->pw_list; s.rs_list = c->rs_list;
+    s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.pwl = c->pwl; s.cls = c->cls; s.pw_list = c->pw_list; s.rs_list = c->rs_list;
     s.scal = c->scal; s.flags = c->flags;
     s.dbg = c->dbg; s.recon = c->opt_recon; s.pw2 = c->opt_pw2;
     return s;
@@ -174,7 +174,7 @@ static inline int drain_grid(const swe_ctx *c) {
 #if SWE_K3_PERSISTENT
     return std::min(nblk(c->nt, kBlock), c->sms * SWE_K3_GRID_PER_SM);
 #else
-    return nblk(c->nt, kBlock);
+    return nblk(c->nt, kBlock * SWE_K3_ILP);
 #endif
 }
 static int launch_check(swe_ctx *c, const char *what) {
@@ -190,7 +190,7 @@ static void destroy_ctx(swe_ctx *c) {
     void *ptrs[] = {c->tt, c->te, c->tp, c->slotL, c->slotR, c->cgeo, c->node, c->en, c->area, c->cb, c->elen, c->dmin,
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
-                    c->cew, c->f0, c->f1, c->f2, c->dti, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
+                    c->cew, c->f0, c->f1, c->f2, c->dti, c->pwl, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
                     c->send_cells, c->recv_cells, c->dbg, c->drain_list};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
@@ -557,7 +557,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(dalloc(&c->ceh, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->ceu, (size_t)3 * nt)); CREATE_TRY(dalloc(&c->cev, (size_t)3 * nt));
     CREATE_TRY(dalloc(&c->cgx, (size_t)nt)); CREATE_TRY(dalloc(&c->cgy, (size_t)nt)); CREATE_TRY(dalloc(&c->pw_list, (size_t)nt)); CREATE_TRY(dalloc(&c->rs_list, (size_t)nt));
     CREATE_TRY(dalloc(&c->f0, (size_t)ne)); CREATE_TRY(dalloc(&c->f1, (size_t)ne)); CREATE_TRY(dalloc(&c->f2, (size_t)ne));
-    CREATE_TRY(dalloc(&c->dti, (size_t)nt)); CREATE_TRY(dalloc(&c->cls, (size_t)nt));
+    CREATE_TRY(dalloc(&c->dti, (size_t)nt)); CREATE_TRY(dalloc(&c->cls, (size_t)nt)); CREATE_TRY(dalloc(&c->pwl, (size_t)nt));
     CREATE_TRY(dalloc(&c->scal, 8)); CREATE_TRY(dalloc(&c->flags, 8));
     CREATE_TRY(dalloc(&c->diag, (size_t)6 * kDiagBlocks + 8));
     for (int q = 0; q < 3; ++q) {
@@ -570,6 +570,7 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(cudaMemset(c->f0, 0, sizeof(double) * ne)); CREATE_TRY(cudaMemset(c->f1, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->f2, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->dti, 0, sizeof(double) * nt)); CREATE_TRY(cudaMemset(c->cls, 0, nt));
+    CREATE_TRY(cudaMemset(c->pwl, 0, sizeof(double) * nt));
     CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 8));
     const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0};  // [0] min_len, [1] dt, [2] time, [3] running min, [4] global min_len
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));

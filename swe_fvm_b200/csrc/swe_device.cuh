@@ -60,9 +60,11 @@ __device__ __noinline__ double bisection(CubicPoly f, double xmin, double xmax) 
     if (sbit(f(xmin)) == sbit(f(xmax))) return (fabs(f(xmin)) < fabs(f(xmax))) ? xmin : xmax;
     int n = 50 + ilog2_trunc(xmax - xmin);
     double x = xmin;
+    bool smin_ = sbit(f(xmin));  // f(xmin) only changes when xmin does: evaluate the cubic once per iteration, same bits
     for (int i = 0; i <= n; i++) {
         x = 0.5 * (xmin + xmax);
-        if (sbit(f(xmin)) != sbit(f(x))) xmax = x; else xmin = x;
+        const bool sx = sbit(f(x));
+        if (smin_ != sx) xmax = x; else { xmin = x; smin_ = sx; }
     }
     return x;
 }

@@ -43,6 +43,7 @@ struct DevFields {
     double *cew;                     // [3*nt] edge-side w, taps only (nullable)
     double *f0, *f1, *f2;            // [ne] fluxes
     double *dti;                     // [nt] draining dt
+    double *pwl;                     // [nt] pass-1 free-surface level of the part-wet cells (PartWet1), read by pass 2
     signed char *cls;                // [nt] 0 dry, 1 part-wet, 2 full-wet
     int *pw_list;                    // [nt] compacted ids of part-wet cells (pass 2 work list)
     int *rs_list;                    // [nt] cells left to the generic reconstruction kernel (K1s)
@@ -182,6 +183,7 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
         const double bmin = smin(smin(P0.z, P1.z), P2.z);
         int br = 0;
         M.o0 = partwet1_level(w, cb, bmax, bmin, &br); M.o1 = u; M.o2 = v;
+        s.pwl[i] = M.o0;  // pass 2 evaluates this cell's pass-1 surface at its nodes: keep the level (up to 50 bisection steps)
         count_branch<TAPS>(s, BR_PW1_SUBMERGED + br);
         s.pw_list[atomicAdd(&s.flags[1], 1)] = i;
     } else {  // ReconstructFullWetCell (:38-84), S2: plane gradients of w, u, v
@@ -631,9 +633,8 @@ __device__ __noinline__ double pass1_w_at_node(const DevMesh &m, const DevFields
     const double4 G = m.cgeo[t];
     const int c = s.cls[t];
     double o0, g0, g1;
-    if (c == 1) {  // PartWet1: flat level, zero gradient (its cgx/cgy may already hold pass-2 values)
-        const double z0 = m.node[m.tp[t]].z, z1 = m.node[m.tp[nt + t]].z, z2 = m.node[m.tp[2 * nt + t]].z;
-        o0 = partwet1_level(s.w[t], G.z, smax(smax(z0, z1), z2), smin(smin(z0, z1), z2), nullptr);
+    if (c == 1) {  // PartWet1: flat level stored by pass 1, zero gradient (its cgx/cgy may already hold pass-2 values)
+        o0 = s.pwl[t];
         g0 = 0.; g1 = 0.;
     } else {
         o0 = (c == 0) ? G.z : s.w[t];
@@ -822,6 +823,9 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
 #ifndef SWE_K3_PERSISTENT
 #define SWE_K3_PERSISTENT 0  // measured: 0.905 ms persistent vs 0.716 ms one cell per short-lived thread at 64M cells
 #endif
+#ifndef SWE_K3_ILP
+#define SWE_K3_ILP 2  // A/B at 64M cells: one cell per thread 0.727 ms, two 0.615 ms
+#endif
 #ifndef SWE_K3_GRID_PER_SM
 #define SWE_K3_GRID_PER_SM 16
 #endif
@@ -845,6 +849,21 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
         if (nx >= nt) break;
         i = nx; t0 = n0; t1 = n1; t2 = n2;
     }
+#elif SWE_K3_ILP == 2
+    // two cells per thread (tiles 2b and 2b + 1 of the block): both cells' edge ids, then both cells' gathers are in
+    // flight together, which halves the number of exposed memory round trips per cell
+    const int i0 = (2 * blockIdx.x) * blockDim.x + threadIdx.x, i1 = i0 + blockDim.x;
+    if (i0 >= nt) return;
+    const bool two = i1 < nt;
+    const int j1 = two ? i1 : i0;
+    const int a0 = __ldg(m.te + i0), a1 = __ldg(m.te + nt + i0), a2 = __ldg(m.te + 2 * nt + i0);
+    const int b0 = __ldg(m.te + j1), b1 = __ldg(m.te + nt + j1), b2 = __ldg(m.te + 2 * nt + j1);
+    const double ha = s.w[i0] - m.cb[i0], hb = s.w[j1] - m.cb[j1];
+    const double aa = m.area[i0], ab = m.area[j1];
+    const double fa0 = s.f0[a0 >= 0 ? a0 : ~a0], fa1 = s.f0[a1 >= 0 ? a1 : ~a1], fa2 = s.f0[a2 >= 0 ? a2 : ~a2];
+    const double fb0 = s.f0[b0 >= 0 ? b0 : ~b0], fb1 = s.f0[b1 >= 0 ? b1 : ~b1], fb2 = s.f0[b2 >= 0 ? b2 : ~b2];
+    st_once(s.dti + i0, drain_dt_cell(ha, aa, a0 >= 0 ? fa0 : -fa0, a1 >= 0 ? fa1 : -fa1, a2 >= 0 ? fa2 : -fa2));
+    if (two) st_once(s.dti + i1, drain_dt_cell(hb, ab, b0 >= 0 ? fb0 : -fb0, b1 >= 0 ? fb1 : -fb1, b2 >= 0 ? fb2 : -fb2));
 #else
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
