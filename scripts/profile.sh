@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${R}_bench_r
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-thacker --no-repro --e2e-steps 2 > gpurun_out/ncu_launches.log 2>&1
 # 3. full capture of the four hot kernels (one launch each, after the warm-up launches)
-ncu --set full --clock-control none --import-source on -k regex:"k_reconstruct|k_flux|k_drain|k_update" -s 24 -c 5 \
+ncu --set full --clock-control none --import-source on -k regex:"k_reconstruct|k_flux|k_drain|k_update" -s 24 -c 11 \
     -o gpurun_out/${R}_prof python bench.py --steps 2 --warmup 3 --no-cpu --no-thacker --no-repro --e2e-steps 2 > gpurun_out/ncu_full.log 2>&1
 # 4. read it (works without a GPU):
 #    ncu -i gpurun_out/${R}_prof.ncu-rep --page raw --csv | python scripts/summarise_profiles.py ...
