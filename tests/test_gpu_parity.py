@@ -357,6 +357,53 @@ def test_k1_forms_are_bit_identical(cases, name, reorder):
         np.testing.assert_array_equal(sd.cell_class(), ref.cell_class())
 
 
+def _delaunay_mesh(seed, npts):
+    """Random Delaunay triangulation of a jittered disc: node degrees 3..10+, ragged boundary, slivers, rough bed."""
+    from scipy.spatial import Delaunay
+    from swe_fvm_b200 import TriangMesh
+    rng = np.random.default_rng(seed)
+    r, th = np.sqrt(rng.uniform(0, 1, npts)) * 3.0, rng.uniform(0, 2 * np.pi, npts)
+    xy = np.stack([4 + r * np.cos(th), 4 + r * np.sin(th)], 1)
+    tri = Delaunay(xy).simplices.astype(np.int64)
+    a, b, c = xy[tri[:, 0]], xy[tri[:, 1]], xy[tri[:, 2]]
+    det = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    tri = tri[np.abs(det) > 1e-9]  # drop degenerate slivers of the hull
+    m = TriangMesh.from_triangles(xy, tri)
+    g = np.asarray(m.geometry)
+    g[:, 2] = 0.25 * ((g[:, 0] - 4) ** 2 + (g[:, 1] - 4) ** 2) / 9.0 + 0.03 * rng.standard_normal(m.nn)
+    return m
+
+
+@pytest.mark.parametrize("seed,npts", [(1, 400), (2, 3000), (3, 12000)])
+@pytest.mark.parametrize("reorder", [False, True])
+def test_random_delaunay_meshes_bit_exact(seed, npts, reorder):
+    """Irregular topology the structured and Gmsh fixtures do not have (node degree 3..10+, boundary triangles with two
+    wall edges, slivers) with rough beds and wet/dry fronts: every stage tap and whole SSPRK3 steps equal the oracle."""
+    from conftest import random_front_state
+    from swe_fvm_b200.solver import Solvers
+    mesh = _delaunay_mesh(seed, npts)
+    T = mesh.centroids()
+    seen = set()
+    for k, level in enumerate((0.05, 0.12, 0.4)):
+        v0 = random_front_state(mesh, T, seed + k, level, amp=0.05)
+        sd, td, ref = _pair(mesh, v0, cor=0.1, reorder=reorder)
+        sd.ComputeInterfaceValues(); ref.compute_interface_values()
+        np.testing.assert_array_equal(sd.cell_class(), ref.cell_class())
+        np.testing.assert_array_equal(sd.node_max_w(), ref.node_max_w())
+        np.testing.assert_array_equal(sd.GetEdgField(), ref.edge_states())
+        np.testing.assert_array_equal(sd.GetSrcField(), ref.sources())
+        sd.ComputeFluxes(); ref.compute_fluxes(1, 2)
+        np.testing.assert_array_equal(sd.GetFluxes(), ref.fluxes())
+        assert sd.GetMinLenToWavespeed() == ref.min_len_to_wavespeed()
+        dt = 0.5 * td.CFLdt()
+        for _ in range(4):
+            Solvers.SSPRK3(td, dt)
+            ref.step(2, 1, 2, dt)
+            np.testing.assert_array_equal(sd.GetVolField(), ref.get_state())
+        seen |= set(np.unique(ref.cell_class()).tolist())
+    assert seen == {0, 1, 2}, "the cases must cover dry, part-wet and full-wet cells"
+
+
 def test_create_rejects_another_local_edge_order():
     """swe_create validates the local convention the kernels rely on (edge k joins nodes k, k+1; neighbour k across it)."""
     from swe_fvm_b200 import StructTriangMesh, SweError
