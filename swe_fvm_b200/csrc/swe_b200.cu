@@ -48,7 +48,19 @@ struct swe_ctx {
     // sit on a 128-cell tile border, so the list pass costs 0.62 ms against 0.73 ms for the full pass, and the fused
     // update needs 104 registers + a barrier (2.75 vs 2.23 ms)
     int opt_fused_drain = 0;
-    int opt_skip_cfl = 1;  // non-final stages of a step run the flux kernel without the CFL minimum (a dead value upstream too)
+    int opt_skip_cfl = 1;
+    // dry-region skipping (DevFields::tile_dry): flags written by K1, usable by K2-K4 while they describe the current state
+    int opt_dry_skip = -1;      // -1 auto: on while >= 20 % of the cells are dry (re-evaluated after the state was set from outside
+                                // and every 1024 steps of a run), 0 off, 1 on. The dry instantiations cost ~5 % on a fully wet mesh
+    bool dry_active = false;    // the dry-region instantiations of K1-K4 are in use
+    bool dry_eval_pending = true;
+    bool k1_dry = false;        // every K1 launch since the last `begin` maintained the flags
+    int64_t steps_since_eval = 0;
+    unsigned char *tile_dry = nullptr, *tile_dry0 = nullptr, *tile_zero = nullptr;  // [ntiles]: this stage / saved state / all zero
+    int ntiles = 0;
+    int64_t state_version = 1, flags_version = 0;  // flags valid iff equal
+    bool flags0_valid = false;
+    int64_t k1_covered = 0;                        // cells reconstructed since the last `begin`  // non-final stages of a step run the flux kernel without the CFL minimum (a dead value upstream too)
     int *drain_list = nullptr;
     int drain_count = 0;
     bool dti_complete = false;  // c->dti holds the draining dt of EVERY cell (full k_drain ran for the last stage)
@@ -164,6 +176,9 @@ static DevFields dev_fields(const swe_ctx *c) {
     s.f0 = c->f0; s.f1 = c->f1; s.f2 = c->f2; s.dti = c->dti; s.pwl = c->pwl; s.cls = c->cls; s.pw_list = c->pw_list; s.rs_list = c->rs_list;
     s.scal = c->scal; s.flags = c->flags;
     s.dbg = c->dbg; s.recon = c->opt_recon; s.pw2 = c->opt_pw2;
+    s.tile_dry = c->tile_dry;
+    s.td = (c->dry_active && c->flags_version == c->state_version) ? c->tile_dry : c->tile_zero;
+    s.td0 = (c->dry_active && c->flags0_valid) ? c->tile_dry0 : c->tile_zero;
     return s;
 }
 
@@ -176,6 +191,30 @@ static inline int drain_grid(const swe_ctx *c) {
 #else
     return nblk(c->nt, kBlock * SWE_K3_ILP);
 #endif
+}
+// dry-region skipping: are the flags of this stage usable right now?
+static inline bool dry_now(const swe_ctx *c) { return c->dry_active && c->flags_version == c->state_version; }
+static int launch_check(swe_ctx *c, const char *what);
+// Decide whether the dry-region instantiations pay off (auto mode). Synchronises the stream once; called from the
+// step / run entry points only when the state was set from outside or a long run asks for a re-evaluation,
+// never during graph capture.
+static int dry_refresh(swe_ctx *c) {
+    if (c->opt_dry_skip >= 0) { c->dry_active = c->opt_dry_skip == 1; c->dry_eval_pending = false; return SWE_OK; }
+    if (!c->dry_eval_pending) return SWE_OK;
+    c->dry_eval_pending = false;
+    c->steps_since_eval = 0;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(c->diag);  // scratch: 8-byte aligned device doubles
+    CUDA_TRY(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+    k_count_dry<<<std::min(nblk(c->nt, 256), 8 * c->sms), 256, 0, c->stream>>>(c->nt, c->cur[0], c->cb, cnt);
+    int rc = launch_check(c, "k_count_dry");
+    if (rc) return rc;
+    unsigned long long h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const bool on = (double)h >= 0.2 * (double)c->nt;
+    if (on != c->dry_active) { c->dry_active = on; c->flags_version = 0; c->flags0_valid = false; }
+    return SWE_OK;
 }
 static int launch_check(swe_ctx *c, const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -191,7 +230,7 @@ static void destroy_ctx(swe_ctx *c) {
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->pwl, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
-                    c->send_cells, c->recv_cells, c->dbg, c->drain_list};
+                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
@@ -240,10 +279,14 @@ static void launch_flux(swe_ctx *c, const DevMesh &m, const DevFields &s, int fl
     const double ac = std::fabs(c->cor);
     const int rf = c->opt_roe_fix, ca = c->opt_cfl_abs;
     const bool opt = rf || ca;  // the default instantiation is upstream as written
+    const bool dry = dry_now(c);
     switch (fluxer_id) {
 #define SWE_X(ID, NAME, TYPE)                                                            \
         case ID:                                                                         \
-            if (!cfl) {                                                                  \
+            if (dry && !opt) {                                                           \
+                if (cfl) k_flux<TYPE, false, true, true><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);  \
+                else k_flux<TYPE, false, false, true><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);     \
+            } else if (!cfl) {                                                           \
                 if (opt) k_flux<TYPE, true, false><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);  \
                 else k_flux<TYPE, false, false><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);     \
             } else if (opt) k_flux<TYPE, true><<<g, kBlock, 0, c->stream>>>(m, s, ac, rf, ca);       \
@@ -270,11 +313,16 @@ static void preload_kernels() {
     SWE_LOAD(k_reconstruct_pf<T, 0>); SWE_LOAD(k_reconstruct_pf<T, 1>); SWE_LOAD(k_reconstruct_pf<T, 2>); \
     SWE_LOAD(k_reconstruct_slow<T>); SWE_LOAD(k_partwet2<T>)
     SWE_LOAD_K1(false); SWE_LOAD_K1(true);
+    SWE_LOAD(k_reconstruct<false, 0, true>); SWE_LOAD(k_reconstruct<false, 1, true>); SWE_LOAD(k_reconstruct<false, 2, true>);
+    SWE_LOAD(k_drain<true>); SWE_LOAD(k_count_dry);
+    SWE_LOAD(k_update<true, true, false, false, true>); SWE_LOAD(k_update<true, false, false, false, true>);
+    SWE_LOAD(k_update<false, true, false, false, true>); SWE_LOAD(k_update<false, false, false, false, true>);
 #define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>); \
-    SWE_LOAD(k_flux<TYPE, false, false>); SWE_LOAD(k_flux<TYPE, true, false>);
+    SWE_LOAD(k_flux<TYPE, false, false>); SWE_LOAD(k_flux<TYPE, true, false>); \
+    SWE_LOAD(k_flux<TYPE, false, true, true>); SWE_LOAD(k_flux<TYPE, false, false, true>);
     SWE_FLUX_LIST(SWE_X)
 #undef SWE_X
-    SWE_LOAD(k_drain); SWE_LOAD(k_drain_list);
+    SWE_LOAD(k_drain<false>); SWE_LOAD(k_drain_list);
     SWE_LOAD(k_update<true, true, false, true>); SWE_LOAD(k_update<true, false, false, true>);
     SWE_LOAD(k_update<false, true, false, true>); SWE_LOAD(k_update<false, false, false, true>);
     SWE_LOAD(k_update<true, true>); SWE_LOAD(k_update<true, false>); SWE_LOAD(k_update<false, true>); SWE_LOAD(k_update<false, false>);
@@ -571,6 +619,10 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(cudaMemset(c->f2, 0, sizeof(double) * ne));
     CREATE_TRY(cudaMemset(c->dti, 0, sizeof(double) * nt)); CREATE_TRY(cudaMemset(c->cls, 0, nt));
     CREATE_TRY(cudaMemset(c->pwl, 0, sizeof(double) * nt));
+    c->ntiles = (int)((nt + kBlock - 1) >> kUpdTileShift);
+    CREATE_TRY(dalloc(&c->tile_dry, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_dry0, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_zero, (size_t)c->ntiles));
+    CREATE_TRY(cudaMemset(c->tile_dry, 0, (size_t)c->ntiles)); CREATE_TRY(cudaMemset(c->tile_dry0, 0, (size_t)c->ntiles));
+    CREATE_TRY(cudaMemset(c->tile_zero, 0, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 8));
     const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0};  // [0] min_len, [1] dt, [2] time, [3] running min, [4] global min_len
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
@@ -630,6 +682,8 @@ SWE_API int swe_set_state_async(swe_ctx *c, const double *prim) {
     int rc = ensure_stage(c, (size_t)3 * c->nt);
     if (rc) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(c->stage_aos, prim, sizeof(double) * 3 * c->nt, cudaMemcpyHostToDevice, c->stream));
+    c->state_version++;
+    c->dry_eval_pending = true;
     k_state_in<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, c->stage_aos, c->cur[0], c->cur[1], c->cur[2]);
     if ((rc = launch_check(c, "k_state_in"))) return rc;
     k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal + 2, 0.0);
@@ -691,6 +745,7 @@ static int pipe_begin(swe_ctx *c, const double *host_in) {
     CUDA_TRY(c, cudaMemcpyAsync(p.in[b], host_in, sizeof(double) * 3 * c->nt, cudaMemcpyHostToDevice, p.s_in));
     CUDA_TRY(c, cudaEventRecord(p.in_ready[b], p.s_in));
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, p.in_ready[b], 0));
+    c->state_version++;
     k_state_in<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, p.in[b], c->cur[0], c->cur[1], c->cur[2]);
     if ((rc = launch_check(c, "k_state_in"))) return rc;
     CUDA_TRY(c, cudaEventRecord(p.in_consumed[b], c->stream));
@@ -771,7 +826,12 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > 2 * SWE_K1_TILED) return bad("0 gather kernel, 1 TMA-staged shared-memory tiles, 2 cp.async software pipeline"); c->opt_tiled = value; }
     else if (!std::strcmp(key, "fused_drain")) { if (value < 0 || value > 1) return bad("0 separate k_drain pass, 1 draining dt fused into the stage update"); c->opt_fused_drain = value; }
     else if (!std::strcmp(key, "skip_cfl")) { if (value < 0 || value > 1) return bad("0 every stage rebuilds the CFL minimum, 1 only the last stage of a step"); c->opt_skip_cfl = value; }
-    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, skip_cfl, graph)");
+    else if (!std::strcmp(key, "dry_skip")) {
+        if (value < -1 || value > 1) return bad("-1 auto (on while >= 20 % of the cells are dry), 0 every tile is processed, 1 tiles of deep-dry cells are skipped by the flux / draining / update kernels");
+        c->opt_dry_skip = value; c->flags_version = 0; c->flags0_valid = false; c->dry_eval_pending = true;
+        if (value >= 0) c->dry_active = value == 1;
+    }
+    else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, skip_cfl, dry_skip, graph)");
     return SWE_OK;
 }
 SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
@@ -783,6 +843,7 @@ SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
     else if (!std::strcmp(key, "k1_tiled")) *value = c->opt_tiled;
     else if (!std::strcmp(key, "fused_drain")) *value = c->opt_fused_drain;
     else if (!std::strcmp(key, "skip_cfl")) *value = c->opt_skip_cfl;
+    else if (!std::strcmp(key, "dry_skip")) *value = c->opt_dry_skip;
     else if (!std::strcmp(key, "graph")) *value = c->opt_graph;
     else { c->err = std::string("swe_get_option: unknown option ") + key; return SWE_ERR_INVALID; }
     return SWE_OK;
@@ -811,7 +872,13 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         CUDA_TRY(c, cudaMemsetAsync(c->flags + 1, 0, sizeof(int), c->stream));
         CUDA_TRY(c, cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
         if (c->taps) CUDA_TRY(c, cudaMemsetAsync(c->dbg, 0, sizeof(unsigned long long) * BR_COUNT, c->stream));
+        // dry-tile flags: preset to "deep dry", cleared by every cell that is not (off: all zero, nothing is skipped)
+        c->k1_dry = c->dry_active && !c->taps && c->opt_tiled == 0;
+        if (c->k1_dry) CUDA_TRY(c, cudaMemsetAsync(c->tile_dry, 1, (size_t)c->ntiles, c->stream));
+        c->k1_covered = 0;
+        c->flags_version = 0;
     }
+    c->k1_covered += std::max(0, last - first);
     if (last > first) {
         int kt = kt_begin(c, KT_RECONSTRUCT);
         // persistent grid: a multiple of the SM count (148 on B200), never more blocks than work
@@ -829,6 +896,10 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
                 if (c->opt_recon == 0) k_reconstruct_tiled<TAPS, 0><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
                 else if (c->opt_recon == 1) k_reconstruct_tiled<TAPS, 1><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
                 else k_reconstruct_tiled<TAPS, 2><<<gt, kTile, 0, c->stream>>>(m, s, first, last); \
+            } else if (!TAPS && c->k1_dry) { \
+                if (c->opt_recon == 0) k_reconstruct<false, 0, true><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+                else if (c->opt_recon == 1) k_reconstruct<false, 1, true><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
+                else k_reconstruct<false, 2, true><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
             } else if (c->opt_recon == 0) k_reconstruct<TAPS, 0><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
             else if (c->opt_recon == 1) k_reconstruct<TAPS, 1><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
             else k_reconstruct<TAPS, 2><<<g1, kK1Block, 0, c->stream>>>(m, s, first, last); \
@@ -858,7 +929,9 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         if (c->taps) k_partwet2<true><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
         else k_partwet2<false><<<kPw2Blocks, kBlock, 0, c->stream>>>(m, s);
         kt_end(c, kt);
-        return launch_check(c, "k_partwet2");
+        if ((rc = launch_check(c, "k_partwet2"))) return rc;
+        // the flags describe the current state once every cell went through pass 1 (ranges may come in any order)
+        if (c->k1_dry && c->k1_covered == (int64_t)c->nt) c->flags_version = c->state_version;
     }
     return SWE_OK;
 }
@@ -906,6 +979,12 @@ SWE_API int swe_save_state(swe_ctx *c) {
     if (!c) return SWE_ERR_INVALID;
     c->sav = c->cur;  // no copy: the next stage update writes the other buffer
     c->saved_pending = true;
+    // the dry-tile flags of the saved state (the non-plain stage updates combine U0 into the result)
+    c->flags0_valid = dry_now(c);
+    if (c->flags0_valid) {
+        CUDA_TRY(c, cudaSetDevice(c->device));
+        CUDA_TRY(c, cudaMemcpyAsync(c->tile_dry0, c->tile_dry, (size_t)c->ntiles, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return SWE_OK;
 }
 
@@ -922,7 +1001,8 @@ static int stage_drain(swe_ctx *c, double ***outb_out) {
             k_drain_list<<<std::min(nblk(c->drain_count, kBlock), c->sms * 16), kBlock, 0, c->stream>>>(m, s, c->drain_list, c->drain_count);
         c->dti_complete = false;
     } else {  // taps: swe_get_draining_dt wants every cell (the fused update still computes its own copy)
-        k_drain<<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
+        if (dry_now(c)) k_drain<true><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
+        else k_drain<false><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
         c->dti_complete = true;
     }
     kt_end(c, kt);
@@ -941,6 +1021,7 @@ static int stage_update_range(swe_ctx *c, double **outb, double a0, double a1, d
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
     const bool fused = c->opt_fused_drain != 0;
+    const bool dry = dry_now(c);
     // fused: one block per ABSOLUTE 128-cell tile touching [first, last)
     const int g = fused ? ((last - 1) >> kUpdTileShift) - (first >> kUpdTileShift) + 1 : nblk(last - first, kBlock);
     const int kt = kt_begin(c, KT_UPDATE);
@@ -948,6 +1029,7 @@ static int stage_update_range(swe_ctx *c, double **outb, double a0, double a1, d
 #define SWE_UPD(PLAIN, COR, W0, U0, V0) \
     do { \
         if (fused) k_update<PLAIN, COR, false, true><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
+        else if (dry) k_update<PLAIN, COR, false, false, true><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
         else k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
     } while (0)
     if (a0 == 0.) {
@@ -965,6 +1047,7 @@ static int stage_update(swe_ctx *c, double a0, double a1, double dt_host, double
     if ((rc = stage_drain(c, &outb))) return rc;
     if ((rc = stage_update_range(c, outb, a0, a1, dt_host, dt_coef, 0, c->nt))) return rc;
     c->cur = outb;
+    c->state_version++;
     return SWE_OK;
 }
 
@@ -1019,7 +1102,9 @@ SWE_API int swe_step(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed
     if (!c) return SWE_ERR_INVALID;
     if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { c->err = "swe_step: unknown scheme"; return SWE_ERR_INVALID; }
     if (!(dt > 0.)) { c->err = "swe_step: dt must be positive"; return SWE_ERR_INVALID; }
-    int rc = one_step(c, scheme, flux, ws, dt, false);
+    int rc = dry_refresh(c);
+    if (rc) return rc;
+    rc = one_step(c, scheme, flux, ws, dt, false);
     if (rc) return rc;
     return swe_advance_dt(c, 0, dt);
 }
@@ -1049,7 +1134,7 @@ static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespe
         return code;
     };
     const int fluxer = c->fluxer >= 0 ? c->fluxer : 3 * (int)flux + (int)ws;
-    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7) | (c->opt_skip_cfl << 10);
+    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7) | (c->opt_skip_cfl << 10) | ((c->dry_active ? 1 : 0) << 11);
     for (int64_t s = 0; s < nsteps; ++s) {
         const int parity = (c->cur == c->bufA) ? 0 : 1;
         swe_ctx::StepGraph *g = nullptr;
@@ -1082,6 +1167,7 @@ static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespe
         c->launches += g->launches;
         // host-side bookkeeping of what the step did to the buffers
         c->cur = g->cur_is_a_after ? c->bufA : c->bufB;
+        c->state_version++;  // the replayed step ended with a stage update: its flags no longer describe the state
         c->sav = (scheme == SWE_EULER) ? c->sav : (parity == 0 ? c->bufA : c->bufB);
         c->saved_pending = false;
     }
@@ -1101,6 +1187,9 @@ SWE_API int swe_run(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespeed 
         if ((rc = read_scalar_fwd(c, 1, &cur))) return rc;
         if (!(cur > 0.)) { c->err = "swe_run: adaptive mode needs dt0 > 0 (no dt stored on the device yet)"; return SWE_ERR_INVALID; }
     }
+    c->steps_since_eval += nsteps;
+    if (c->steps_since_eval >= 1024) c->dry_eval_pending = true;  // the shoreline moves: look again now and then
+    if ((rc = dry_refresh(c))) return rc;
     const bool use_graph = (c->opt_graph == 1 || (c->opt_graph < 0 && c->nt <= kGraphAutoCells)) && !c->ktiming && nsteps >= 4;
     if (use_graph) return run_graphed(c, scheme, flux, ws, nsteps, dt, adaptive);
     for (int64_t s = 0; s < nsteps; ++s) {
@@ -1249,7 +1338,7 @@ SWE_API int swe_compute_rhs(swe_ctx *c, double dt, double *rhs) {
     if (rc) return rc;
     const DevMesh m = dev_mesh(c);
     const DevFields s = dev_fields(c);
-    k_drain<<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
+    k_drain<false><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
     if ((rc = launch_check(c, "k_drain"))) return rc;
     c->dti_complete = true;
     double *r0 = c->stage_aos, *r1 = r0 + c->nt, *r2 = r1 + c->nt, *aos = r2 + c->nt;
@@ -1355,6 +1444,8 @@ SWE_API int swe_kernel_times(swe_ctx *c, int32_t max_kinds, double *ms_total, in
 SWE_API int swe_case_set_bathymetry_device(swe_ctx *c, const swe_case *cs) {
     if (!c || !cs || cs->kind < 0 || cs->kind > SWE_CASE_BOWL_HUMP) return SWE_ERR_INVALID;
     CUDA_TRY(c, cudaSetDevice(c->device));
+    c->state_version++;  // the bed (and with it every cell class) changes
+    c->dry_eval_pending = true;
     k_case_bathymetry<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->node, *cs);
     int rc;
     if ((rc = launch_check(c, "k_case_bathymetry"))) return rc;
@@ -1365,6 +1456,8 @@ SWE_API int swe_case_set_bathymetry_device(swe_ctx *c, const swe_case *cs) {
 SWE_API int swe_case_initial_state_device(swe_ctx *c, const swe_case *cs, int32_t quad_n, double t) {
     if (!c || !cs || quad_n < 1 || cs->kind < 0 || cs->kind > SWE_CASE_BOWL_HUMP) return SWE_ERR_INVALID;
     CUDA_TRY(c, cudaSetDevice(c->device));
+    c->state_version++;
+    c->dry_eval_pending = true;
     k_case_init<<<nblk(c->nt, 128), 128, 0, c->stream>>>(dev_mesh(c), *cs, quad_n, t, c->cur[0], c->cur[1], c->cur[2]);
     int rc;
     if ((rc = launch_check(c, "k_case_init"))) return rc;
@@ -1443,6 +1536,7 @@ SWE_API int swe_halo_unpack(swe_ctx *c, const double *buf) {
     if (!c || (c->nrecv && !buf)) return SWE_ERR_INVALID;
     if (c->nrecv == 0) return SWE_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
+    c->state_version++;
     k_halo_unpack<<<nblk(c->nrecv, 256), 256, 0, c->stream>>>(c->nrecv, c->recv_cells, buf, c->cur[0], c->cur[1], c->cur[2]);
     return launch_check(c, "k_halo_unpack");
 }
@@ -1523,6 +1617,7 @@ SWE_API int swe_halo_p2p_pull(swe_ctx *c) {
     k_halo_wait<<<1, 32, 0, c->stream>>>(c->p2p_flags, (int)c->p2p_peers.size(), seq, 20000000000ll, c->flags + 5);
     if ((rc = launch_check(c, "k_halo_wait"))) return rc;
     if (c->nrecv > 0) {
+        c->state_version++;
         k_halo_unpack<<<nblk(c->nrecv, 256), 256, 0, c->stream>>>(c->nrecv, c->recv_cells, c->p2p_recv[seq & 1], c->cur[0], c->cur[1], c->cur[2]);
         if ((rc = launch_check(c, "k_halo_unpack"))) return rc;
     }

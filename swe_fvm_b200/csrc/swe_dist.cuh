@@ -219,6 +219,7 @@ static int dist_pull(swe_dist *d) {  // wait for every peer's flag, unpack into 
     d->pending = false;
     const int g = std::max(1, std::min(nblk(d->nrecv, 256), 4 * c->sms));
     const int kt = kt_begin(c, KT_HALO_WAIT);  // includes the time spent waiting for a slower neighbour
+    c->state_version++;  // halo cells change
     k_halo_wait_unpack<<<g, 256, 0, c->stream>>>(d->halo_flags(), (int)d->peers.size(), d->seq, d->timeout_cycles, c->flags + 5,
                                                  d->nrecv, c->recv_cells, d->recvbuf[d->seq & 1], c->cur[0], c->cur[1], c->cur[2]);
     kt_end(c, kt);
@@ -283,10 +284,12 @@ static int dist_stage(swe_dist *d, swe_flux flux, swe_wavespeed ws, double a0, d
         if ((rc = dist_push(d, outb))) return rc;
         DIST_CTX(d, stage_update_range(c, outb, a0, a1, dt_host, dt_coef, c->class_first[0], c->class_first[1]));
         c->cur = outb;  // only now: the stage input (c->cur) had to stay in place for the second range
+        c->state_version++;
         // class 3 (halo cells) is not updated: every halo cell is overwritten by the exchange
     } else {
         DIST_CTX(d, stage_update_range(c, outb, a0, a1, dt_host, dt_coef, 0, c->class_first[3]));
         c->cur = outb;
+        c->state_version++;
         if (world > 1) {
             if ((rc = dist_push(d, c->cur))) return rc;
             if ((rc = dist_pull(d))) return rc;
@@ -382,6 +385,7 @@ SWE_API int swe_dist_step(swe_dist *d, swe_scheme scheme, swe_flux flux, swe_wav
     if (scheme < SWE_EULER || scheme > SWE_SSPRK3) { d->err = "swe_dist_step: unknown scheme"; return SWE_ERR_INVALID; }
     if (!(dt > 0.)) { d->err = "swe_dist_step: dt must be positive"; return SWE_ERR_INVALID; }
     DIST_TRY(d, cudaSetDevice(d->ctx->device));
+    DIST_CTX(d, dry_refresh(d->ctx));
     int rc = dist_one_step(d, scheme, flux, ws, dt, false);
     if (rc) return rc;
     d->min_pending = true; d->min_adaptive = 0; d->min_dt_fixed = dt;
@@ -395,6 +399,9 @@ static int dist_run_begin(swe_dist *d, swe_scheme scheme, double dt, double dt0)
     DIST_TRY(d, cudaSetDevice(d->ctx->device));
     int rc = dist_finish_min(d, true);
     if (rc) return rc;
+    // dry-region instantiations or not: decided here, where everything issued so far has its matching peer work
+    // issued too (the evaluation synchronises this rank's stream once after the state was set from outside)
+    DIST_CTX(d, dry_refresh(d->ctx));
     if (!(dt > 0.)) DIST_CTX(d, swe_set_dt(d->ctx, dt0));
     return SWE_OK;
 }

@@ -44,6 +44,14 @@ struct DevFields {
     double *f0, *f1, *f2;            // [ne] fluxes
     double *dti;                     // [nt] draining dt
     double *pwl;                     // [nt] pass-1 free-surface level of the part-wet cells (PartWet1), read by pass 2
+    // Dry-region skipping. tile_dry[t] (written by K1, preset to 1) stays 1 iff EVERY cell of the 128-cell tile t is
+    // "deep dry" in the stage-begin state: dry, stored canonically as (cb, +0, +0), and all its edge neighbours dry. Then
+    // every flux through its edges is exactly +0, its draining dt is 0 and the stage update returns (cb, +0, +0) again,
+    // so K2 writes zeros without reading the edge states, K3 writes 0 and K4 leaves the tile alone — bit-identical to
+    // doing the work. td / td0: the flags K2-K4 may use for this stage / for the state saved by swe_save_state (an
+    // all-zero array when they do not describe the current data).
+    unsigned char *tile_dry;
+    const unsigned char *td, *td0;
     signed char *cls;                // [nt] 0 dry, 1 part-wet, 2 full-wet
     int *pw_list;                    // [nt] compacted ids of part-wet cells (pass 2 work list)
     int *rs_list;                    // [nt] cells left to the generic reconstruction kernel (K1s)
@@ -61,7 +69,12 @@ template <bool TAPS> __device__ __forceinline__ void count_branch(const DevField
     if (TAPS) atomicAdd(&s.dbg[b], 1ull);
 }
 
+#ifndef SWE_K1_SPLIT
+#define SWE_K1_SPLIT 1
+#endif
 constexpr int kBlock = 128;
+constexpr int kUpdTileShift = 7;  // tiles of kBlock = 128 consecutive cells (device numbering): stage update blocks, dry-region flags
+static_assert((1 << kUpdTileShift) == kBlock, "tile = one thread block of the stage update");
 
 // stores of write-once intermediates (edge-side values, gradients, fluxes, dti) may carry the
 // evict-first hint so that they do not displace the gathered neighbour data in L2 (SWE_STCS=1)
@@ -173,6 +186,9 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
     const bool dry = !is_wet(w - cb);
     const bool full = !bnd && (bmax < w);
     s.cls[i] = dry ? 0 : (full ? 2 : 1);
+#if !SWE_K1_SPLIT
+    s.tile_dry[i >> kUpdTileShift] = 0;  // the generic routine does not classify tiles: nothing is skipped
+#endif
 
     Muscl M;
     M.g00 = M.g01 = M.g10 = M.g11 = M.g20 = M.g21 = 0.;
@@ -270,19 +286,22 @@ __device__ __forceinline__ void reconstruct_cell(const DevMesh &m, const DevFiel
 // the support values the neighbour means, which needs fewer registers and selects. Every other
 // cell (part-wet cells, full-wet cells next to a dry / part-wet one) is appended to rs_list and
 // reconstructed by the generic routine in k_reconstruct_slow — same formulas, same bits.
-#ifndef SWE_K1_SPLIT
-#define SWE_K1_SPLIT 1
-#endif
 // arithmetic of the fast path on already loaded data (shared by the gather kernel and the tiled kernel)
-template <bool TAPS, int RECON>
-__device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, const int i, const bool bnd, const double4 P0,
+template <bool TAPS, int RECON, bool DRY = false>
+__device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, const int i, const int wall, const double4 P0,
                                              const double4 P1, const double4 P2, const double4 Gi, const double w,
                                              const double u, const double v, const double N00, const double N01,
                                              const double N02, const double N10, const double N11, const double N12,
                                              const double N20, const double N21, const double N22, const double4 G0,
                                              const double4 G1, const double4 G2);
+// DRY: bit k set iff side k of the cell is a wall (no neighbour); otherwise only "any side is a wall" matters
+template <bool DRY>
+__device__ __forceinline__ int wall_mask(int it0, int it1, int it2) {
+    if (DRY) return (it0 < 0 ? 1 : 0) | (it1 < 0 ? 2 : 0) | (it2 < 0 ? 4 : 0);
+    return ((it0 | it1 | it2) < 0) ? 1 : 0;
+}
 
-template <bool TAPS, int RECON>
+template <bool TAPS, int RECON, bool DRY>
 __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const DevFields &s, const int i, const int ip0,
                                                       const int ip1, const int ip2, const int it0, const int it1,
                                                       const int it2) {
@@ -294,19 +313,27 @@ __device__ __forceinline__ bool reconstruct_cell_fast(const DevMesh &m, const De
     const double N10 = __ldg(s.w + j1), N11 = __ldg(s.u + j1), N12 = __ldg(s.v + j1);
     const double N20 = __ldg(s.w + j2), N21 = __ldg(s.u + j2), N22 = __ldg(s.v + j2);
     const double4 G0 = ldg4(m.cgeo + j0), G1 = ldg4(m.cgeo + j1), G2 = ldg4(m.cgeo + j2);
-    return fast_compute<TAPS, RECON>(s, m.nt, i, (it0 | it1 | it2) < 0, P0, P1, P2, Gi, w, u, v, N00, N01, N02, N10, N11, N12,
-                                     N20, N21, N22, G0, G1, G2);
+    return fast_compute<TAPS, RECON, DRY>(s, m.nt, i, wall_mask<DRY>(it0, it1, it2), P0, P1, P2, Gi, w, u, v, N00, N01, N02, N10, N11,
+                                          N12, N20, N21, N22, G0, G1, G2);
 }
 
-template <bool TAPS, int RECON>
-__device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, const int i, const bool bnd, const double4 P0,
+template <bool TAPS, int RECON, bool DRY>
+__device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, const int i, const int wall, const double4 P0,
                                              const double4 P1, const double4 P2, const double4 Gi, const double w,
                                              const double u, const double v, const double N00, const double N01,
                                              const double N02, const double N10, const double N11, const double N12,
                                              const double N20, const double N21, const double N22, const double4 G0,
                                              const double4 G1, const double4 G2) {
     const double cx = Gi.x, cy = Gi.y, cb = Gi.z;
+    const bool bnd = wall != 0;
     const bool dry = !is_wet(w - cb);
+    if (DRY) {  // deep-dry test for the tile flag (see DevFields::tile_dry): one cell that fails clears its tile
+        const bool canon = __double_as_longlong(w) == __double_as_longlong(cb) && __double_as_longlong(u) == 0ll &&
+                           __double_as_longlong(v) == 0ll;
+        const bool nb_dry = ((wall & 1) || !is_wet(N00 - G0.z)) && ((wall & 2) || !is_wet(N10 - G1.z)) &&
+                            ((wall & 4) || !is_wet(N20 - G2.z));
+        if (!(canon && nb_dry)) s.tile_dry[i >> kUpdTileShift] = 0;
+    }
     const bool full = !bnd && (smax(smax(P0.z, P1.z), P2.z) < w);
     const bool nbfull = (G0.w < N00) && (G1.w < N10) && (G2.w < N20);
     if (!dry && !(full && nbfull)) return false;
@@ -384,7 +411,9 @@ __global__ void __launch_bounds__(kBlock) k_reconstruct_slow(DevMesh m, DevField
 
 // persistent grid-stride kernel over the cell range [first, last); the ids of the thread's next
 // cell are fetched before the current cell is processed (hides the first memory round trip)
-template <bool TAPS, int RECON>
+// DRY: the instantiation that also maintains the dry-tile flags (DevFields::tile_dry); used while a sizeable part of the
+// domain is dry (the flag logic costs ~3 % here and 5-8 % in K2 / K4 on a fully wet mesh, measured)
+template <bool TAPS, int RECON, bool DRY = false>
 __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(DevMesh m, DevFields s, int first, int last) {
     const int nt = m.nt;
     const int stride = gridDim.x * blockDim.x;
@@ -400,7 +429,7 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(Dev
             nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
         }
 #if SWE_K1_SPLIT
-        if (!reconstruct_cell_fast<TAPS, RECON>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
+        if (!reconstruct_cell_fast<TAPS, RECON, DRY>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
 #else
         reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
 #endif
@@ -521,7 +550,7 @@ __global__ void __launch_bounds__(kTile, SWE_K1_MIN_BLOCKS) k_reconstruct_tiled(
             else { A = __ldg(s.w + J); B = __ldg(s.u + J); C = __ldg(s.v + J); G = ldg4(m.cgeo + J); }
             SWE_NB(j0, N00, N01, N02, G0) SWE_NB(j1, N10, N11, N12, G1) SWE_NB(j2, N20, N21, N22, G2)
 #undef SWE_NB
-            if (!fast_compute<TAPS, RECON>(s, nt, i, (it0 | it1 | it2) < 0, P0, P1, P2, st.cgeo[tid], st.w[tid], st.u[tid], st.v[tid],
+            if (!fast_compute<TAPS, RECON>(s, nt, i, wall_mask<false>(it0, it1, it2), P0, P1, P2, st.cgeo[tid], st.w[tid], st.u[tid], st.v[tid],
                                            N00, N01, N02, N10, N11, N12, N20, N21, N22, G0, G1, G2))
                 s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
         }
@@ -608,7 +637,7 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct_pf(
         const double N10 = st.st[3][tid], N11 = st.st[4][tid], N12 = st.st[5][tid];
         const double N20 = st.st[6][tid], N21 = st.st[7][tid], N22 = st.st[8][tid];
         const double w = st.st[9][tid], u = st.st[10][tid], v = st.st[11][tid];
-        const bool bnd = (it0 | it1 | it2) < 0;
+        const int bnd = wall_mask<false>(it0, it1, it2);
         const bool more = nx < last;
         if (more) {  // the slots are free again: start the copies of the next cell, then fetch the ids of the one after
             k1pf_issue(m, s, st, tid, nx, np0, np1, np2, nt0, nt1, nt2);
@@ -629,7 +658,6 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct_pf(
 // Value at node Q = (qx, qy, qz) of cell t's PASS-1 reconstruction, i.e. one term of the max in
 // m_max_wp[node] = max(m_max_wp[node], muscl.AtPoint(P(node))[0]) (src/SpaceDisc.cpp:23).
 __device__ __noinline__ double pass1_w_at_node(const DevMesh &m, const DevFields &s, int t, double qx, double qy, double qz) {
-    const int nt = m.nt;
     const double4 G = m.cgeo[t];
     const int c = s.cls[t];
     double o0, g0, g1;
@@ -753,6 +781,25 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
+// read-only int32 load that the compiler may not sink below a later branch (asm volatile): used where a load must be
+// in flight BEFORE a dry-tile test so that wet tiles do not pay an extra memory round trip for the test
+__device__ __forceinline__ int ldg_i32_early(const int *p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));  // volatile at the PTX level too: ptxas keeps program order
+    return v;
+}
+// cell of a cell-major slot (slot = k * nt + i, k in 0..2) and the dry-tile test of an edge (see DevFields::tile_dry)
+__device__ __forceinline__ int slot_cell(int slot, int nt) {
+    int i = slot;
+    if (i >= nt) i -= nt;
+    if (i >= nt) i -= nt;
+    return i;
+}
+__device__ __forceinline__ bool edge_in_dry_tile(const unsigned char *td, int nt, int sl, int sr) {
+    unsigned f = __ldg(td + (slot_cell(sl, nt) >> kUpdTileShift));
+    if (sr >= 0) f |= __ldg(td + (slot_cell(sr, nt) >> kUpdTileShift));
+    return f != 0;
+}
 #ifndef SWE_K2_GRID_PER_SM
 #define SWE_K2_GRID_PER_SM 64  // A/B at 64M cells: 16 -> 2.114 ms, 64 -> 2.062 ms, one block per 128 edges -> 2.889 ms
 #endif
@@ -762,34 +809,69 @@ __device__ __forceinline__ double warp_min(double v) {
 // CFL = false: the instantiation for the non-final stages of a multi-stage step. m_min_length_to_wavespeed is reset
 // and rebuilt by EVERY ComputeFluxes (src/SpaceDisc.cpp:56) and only read after the step (CFLdt, include/TimeDisc.h:13),
 // so the minima of the earlier stages are dead values: no dmin load, no division, no reduction, no publish.
-template <class FLUXER, bool OPT, bool CFL = true>
+template <class FLUXER, bool OPT, bool CFL = true, bool DRY = false>
 __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, DevFields s, double abscor, int roe_fix, int cfl_abs) {
     const int ne = m.ne;
     const int stride = gridDim.x * blockDim.x;
     double l2w = 1.0;  // reset value of m_min_length_to_wavespeed (:56)
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < ne) {
+    if (!DRY) {
+        if (e < ne) {
+            int sl = __ldg(m.slotL + e), sr = __ldg(m.slotR + e);
+            for (;;) {
+                const int nx = e + stride;
+                int nsl = 0, nsr = 0;
+                if (nx < ne) { nsl = __ldg(m.slotL + nx); nsr = __ldg(m.slotR + nx); }
+                const double2 n = __ldg(m.en + e);
+                double f0, f1, f2;
+                if (sr < 0) {  // SOLID_WALL: ElemFlux(n, {h(lf), 0, 0}) with the cell-mean depth (:67-69)
+                    const int lf = sl % m.nt;
+                    const double h = s.w[lf] - m.cb[lf];
+                    elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
+                } else {
+                    double cand = 1.0;
+                    FLUXER::template eval<OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
+                                               __ldg(s.ceu + sr), __ldg(s.cev + sr), CFL ? __ldg(m.dmin + e) : 1.0, abscor, f0, f1, f2,
+                                               cand, roe_fix, cfl_abs);
+                    if (CFL) l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
+                }
+                st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
+                if (nx >= ne) break;
+                e = nx; sl = nsl; sr = nsr;
+            }
+        }
+    } else if (e < ne) {
+        // dry-region form: slot ids two edges ahead, dry-tile flags one edge ahead, so neither is on the critical path
         int sl = __ldg(m.slotL + e), sr = __ldg(m.slotR + e);
+        int nx = e + stride;
+        int nsl = 0, nsr = 0;
+        if (nx < ne) { nsl = __ldg(m.slotL + nx); nsr = __ldg(m.slotR + nx); }
+        bool skip = edge_in_dry_tile(s.td, m.nt, sl, sr);
         for (;;) {
-            const int nx = e + stride;
-            int nsl = 0, nsr = 0;
-            if (nx < ne) { nsl = __ldg(m.slotL + nx); nsr = __ldg(m.slotR + nx); }
-            const double2 n = __ldg(m.en + e);
+            const int n2 = nx + stride;
+            int n2sl = 0, n2sr = 0;
+            if (n2 < ne) { n2sl = __ldg(m.slotL + n2); n2sr = __ldg(m.slotR + n2); }
+            const bool nskip = (nx < ne) && edge_in_dry_tile(s.td, m.nt, nsl, nsr);
             double f0, f1, f2;
-            if (sr < 0) {  // SOLID_WALL: ElemFlux(n, {h(lf), 0, 0}) with the cell-mean depth (:67-69)
-                const int lf = sl % m.nt;
-                const double h = s.w[lf] - m.cb[lf];
-                elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
+            if (skip) {  // a cell of a deep-dry tile on either side: both cells are dry, the flux is exactly +0
+                f0 = 0.; f1 = 0.; f2 = 0.;
             } else {
-                double cand = 1.0;
-                FLUXER::template eval<OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
-                                           __ldg(s.ceu + sr), __ldg(s.cev + sr), CFL ? __ldg(m.dmin + e) : 1.0, abscor, f0, f1, f2,
-                                           cand, roe_fix, cfl_abs);
-                if (CFL) l2w = (cand < l2w) ? cand : l2w;  // edges excluded from the CFL min carry dmin = +inf
+                const double2 n = __ldg(m.en + e);
+                if (sr < 0) {
+                    const int lf = sl % m.nt;
+                    const double h = s.w[lf] - m.cb[lf];
+                    elem_flux(n.x, n.y, h, 0., 0., f0, f1, f2);
+                } else {
+                    double cand = 1.0;
+                    FLUXER::template eval<OPT>(n.x, n.y, __ldg(s.ceh + sl), __ldg(s.ceu + sl), __ldg(s.cev + sl), __ldg(s.ceh + sr),
+                                               __ldg(s.ceu + sr), __ldg(s.cev + sr), CFL ? __ldg(m.dmin + e) : 1.0, abscor, f0, f1, f2,
+                                               cand, roe_fix, cfl_abs);
+                    if (CFL) l2w = (cand < l2w) ? cand : l2w;
+                }
             }
             st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
             if (nx >= ne) break;
-            e = nx; sl = nsl; sr = nsr;
+            e = nx; nx = n2; sl = nsl; sr = nsr; nsl = n2sl; nsr = n2sr; skip = nskip;
         }
     }
     if (!CFL) return;
@@ -830,6 +912,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
 #define SWE_K3_GRID_PER_SM 16
 #endif
 __device__ __forceinline__ double drain_dt_cell(double h, double area, double fe0, double fe1, double fe2);
+template <bool DRY = false>
 __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
     const int nt = m.nt;
 #if SWE_K3_PERSISTENT
@@ -856,8 +939,21 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
     if (i0 >= nt) return;
     const bool two = i1 < nt;
     const int j1 = two ? i1 : i0;
-    const int a0 = __ldg(m.te + i0), a1 = __ldg(m.te + nt + i0), a2 = __ldg(m.te + 2 * nt + i0);
-    const int b0 = __ldg(m.te + j1), b1 = __ldg(m.te + nt + j1), b2 = __ldg(m.te + 2 * nt + j1);
+    int a0, a1, a2, b0, b1, b2;
+    if (DRY) {
+        // the dry-tile flags travel with the edge ids (no extra round trip for wet tiles); tested before the flux gathers
+        const unsigned dry_a = __ldg(s.td + (i0 >> kUpdTileShift)), dry_b = __ldg(s.td + (j1 >> kUpdTileShift));
+        a0 = ldg_i32_early(m.te + i0); a1 = ldg_i32_early(m.te + nt + i0); a2 = ldg_i32_early(m.te + 2 * nt + i0);
+        b0 = ldg_i32_early(m.te + j1); b1 = ldg_i32_early(m.te + nt + j1); b2 = ldg_i32_early(m.te + 2 * nt + j1);
+        if (dry_a && dry_b) {  // deep-dry tiles: dry cells, draining dt = 0
+            st_once(s.dti + i0, 0.);
+            if (two) st_once(s.dti + i1, 0.);
+            return;
+        }
+    } else {
+        a0 = __ldg(m.te + i0); a1 = __ldg(m.te + nt + i0); a2 = __ldg(m.te + 2 * nt + i0);
+        b0 = __ldg(m.te + j1); b1 = __ldg(m.te + nt + j1); b2 = __ldg(m.te + 2 * nt + j1);
+    }
     const double ha = s.w[i0] - m.cb[i0], hb = s.w[j1] - m.cb[j1];
     const double aa = m.area[i0], ab = m.area[j1];
     const double fa0 = s.f0[a0 >= 0 ? a0 : ~a0], fa1 = s.f0[a1 >= 0 ? a1 : ~a1], fa2 = s.f0[a2 >= 0 ? a2 : ~a2];
@@ -910,8 +1006,6 @@ struct ClassFirst { int f[6]; };
 __device__ __forceinline__ int class_of(const ClassFirst &cf, int i) {
     return (i >= cf.f[1]) + (i >= cf.f[2]) + (i >= cf.f[3]) + (i >= cf.f[4]);
 }
-constexpr int kUpdTileShift = 7;  // the stage update works on tiles of kBlock = 128 consecutive cells
-static_assert((1 << kUpdTileShift) == kBlock, "update tile = one thread block");
 __global__ void k_mark_drain_boundary(int nt, const int *tt, ClassFirst cf, unsigned char *flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
@@ -941,7 +1035,7 @@ __global__ void k_mark_drain_boundary(int nt, const int *tt, ClassFirst cf, unsi
 // same tile (and inside [first, last)) is served from shared memory and only the few neighbours outside read the
 // global dti array, which k_drain_list filled for exactly those cells. Saves the k_drain pass over all cells and
 // three 8-byte gathers per cell.
-template <bool PLAIN, bool COR, bool RHS_ONLY = false, bool FUSED = false>
+template <bool PLAIN, bool COR, bool RHS_ONLY = false, bool FUSED = false, bool DRY = false>
 __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m, DevFields s, const double *__restrict__ w0,
                                                    const double *__restrict__ u0, const double *__restrict__ v0,
                                                    double *wout, double *uout, double *vout, double a0, double a1,
@@ -954,13 +1048,24 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     const bool active = FUSED ? (i >= first && i < last) : true;
     if (!FUSED) { if (i >= last) return; }
     else if (!active) i = first;  // idle lanes of a partial tile shadow a valid cell (loads stay in bounds), never store
+    // dry-tile flags: loaded together with the cell's own (coalesced) data, tested before the gathers, so a wet tile
+    // pays no extra memory round trip and a deep-dry tile skips the edge / neighbour gathers
+    unsigned skip_t = 0;
+    if (DRY) {
+        const int t = i >> kUpdTileShift;
+        skip_t = __ldg(s.td + t);
+        if (!PLAIN) skip_t &= __ldg(s.td0 + t);
+    }
     // All loads are issued before any arithmetic (ids -> gathers: two dependent round trips, every
     // gather of the cell in flight at once). Written out explicitly because the compiler's own
     // schedule flipped between a batched (2.2 ms) and an interleaved (2.6 ms at 64M cells) form
     // when an unrelated kernel parameter changed.
     int te[3], tn[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { te[k] = __ldg(m.te + k * nt + i); tn[k] = __ldg(m.tt + k * nt + i); }
+    for (int k = 0; k < 3; ++k) {
+        if (DRY) { te[k] = ldg_i32_early(m.te + k * nt + i); tn[k] = ldg_i32_early(m.tt + k * nt + i); }
+        else { te[k] = __ldg(m.te + k * nt + i); tn[k] = __ldg(m.tt + k * nt + i); }
+    }
     // dt_coef != 0: stage dt = dt_coef * (device-resident dt), else the host value
     const double dt = (dt_coef != 0.) ? dt_coef * s.scal[1] : dt_host;
     const double cb = __ldg(m.cb + i);
@@ -970,6 +1075,11 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     const double wc = s.w[i], uc = s.u[i], vc = s.v[i];
     double wa = 0., ua = 0., va = 0.;
     if (!PLAIN) { wa = w0[i]; ua = u0[i]; va = v0[i]; }
+    if (DRY && skip_t) {
+        // deep-dry tile now (and, when U0 enters the combination, at swe_save_state): the cell stays (cb, +0, +0)
+        if (wout != s.w) { wout[i] = cb; uout[i] = 0.; vout[i] = 0.; }  // out of place (first stage after swe_save_state)
+        return;
+    }
     double F0[3], F1[3], F2[3], dtn[3], len[3], hek[3], cu[3], cv[3];
     double2 nrm[3];
     const int lo_t = max(base, first), hi_t = min(base + kBlock, last);  // FUSED: cells whose dti this block computes
@@ -1040,6 +1150,15 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     }
     if (!(isfinite(ow) && isfinite(ou) && isfinite(ov))) s.flags[0] = 1;
     wout[i] = ow; uout[i] = ou; vout[i] = ov;
+}
+
+// number of dry cells of the current state (decides whether the dry-region instantiations are worth their overhead)
+__global__ void k_count_dry(int nt, const double *w, const double *cb, unsigned long long *out) {
+    unsigned long long n = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) n += is_wet(w[i] - cb[i]) ? 0 : 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
 }
 
 // IsDryCell / IsFullWetCell / IsPartWetCell (src/MUSCLObject.cpp:13-29) of the CURRENT state, without reconstructing

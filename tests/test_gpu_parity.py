@@ -404,6 +404,53 @@ def test_random_delaunay_meshes_bit_exact(seed, npts, reorder):
     assert seen == {0, 1, 2}, "the cases must cover dry, part-wet and full-wet cells"
 
 
+@pytest.mark.parametrize("scheme", ["euler", "ssprk2", "ssprk3"])
+@pytest.mark.parametrize("reorder", [False, True])
+def test_dry_region_skipping_is_bit_identical(scheme, reorder):
+    """Tiles of 128 deep-dry cells (dry, stored as (cb, +0, +0), all neighbours dry) are skipped by the flux / draining-dt /
+    update kernels. Same bits as doing the work and as the oracle while the shoreline of a Thacker basin sweeps over the
+    tiles (wetting and drying), from a start state whose dry cells are NOT canonical (|h| <= 1e-12, -0.0, non-zero
+    velocities), through swe_run (graph replay and plain launches) and single steps."""
+    from swe_fvm_b200 import capi
+    from swe_fvm_b200.solver import Solvers, SpaceDisc, TimeDisc
+    from oracle.oracle import Oracle
+    mesh, case, v0 = make_case("classic_thacker", 96, quad_n=4)
+    v0 = v0.copy()
+    T = mesh.centroids()
+    dry = (v0[:, 0] - T[:, 2]) <= 1e-12
+    rng = np.random.default_rng(5)
+    k = np.nonzero(dry)[0]
+    v0[k[::3], 0] += 7e-13                    # dry but not canonical: the first update must still canonicalise them
+    v0[k[1::3], 0] -= 3e-13
+    v0[k[::5], 1] = -0.0
+    v0[k[2::7], 2] = 0.25 * rng.standard_normal(len(k[2::7]))
+    ref = Oracle(mesh, cor=0.05)
+    ref.set_state(v0)
+    runs = []
+    for skip, graph in ((1, 0), (0, 0), (1, 1)):
+        sd = SpaceDisc("hllc", "einfeldt", mesh, v0, cor=0.05, reorder=reorder)
+        sd.set_option("dry_skip", skip)
+        sd.set_option("graph", graph)
+        assert sd.get_option("dry_skip") == skip
+        runs.append((sd, TimeDisc(sd)))
+    sc = SCHEMES[scheme]
+    dt = 4e-3
+    for block in range(6):
+        for _ in range(25):
+            ref.step(sc, 1, 2, dt)
+        for sd, td in runs:
+            Solvers.run(td, scheme, 24, dt=dt)
+            getattr(Solvers, {"euler": "Euler", "ssprk2": "SSPRK2", "ssprk3": "SSPRK3"}[scheme])(td, dt)
+            got = sd.GetVolField()
+            np.testing.assert_array_equal(got.view(np.uint64), ref.get_state().view(np.uint64))
+            assert td.CFLdt() == ref.cfl_dt()
+    # the shoreline moved: some cells changed between dry and wet during the run, and most tiles were skipped
+    ref.compute_interface_values()
+    cls = ref.cell_class()
+    assert (cls == 0).mean() > 0.5 and (cls == 2).any() and (cls == 1).any()
+    assert ((cls == 0) != dry).any()
+
+
 def test_create_rejects_another_local_edge_order():
     """swe_create validates the local convention the kernels rely on (edge k joins nodes k, k+1; neighbour k across it)."""
     from swe_fvm_b200 import StructTriangMesh, SweError
