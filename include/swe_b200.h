@@ -201,7 +201,12 @@ SWE_API int swe_set_fluxer(swe_ctx *ctx, int32_t id);
  *   "graph"       -1 replay whole steps as a CUDA graph on meshes below 4M cells (default) | 0 off | 1 on
  *   "k1_tiled"    0 register-prefetched gather reconstruction (default) | 1 TMA-staged shared-memory tiles
  *   "fused_drain" 0 separate draining-dt pass (default) | 1 draining dt computed inside the stage update
- *                 (swe_get_draining_dt then needs swe_enable_taps or swe_compute_rhs) */
+ *                 (swe_get_draining_dt then needs swe_enable_taps or swe_compute_rhs)
+ *   "skip_cfl"    1 only the last stage of a step rebuilds the CFL minimum (default; the earlier ones are dead values
+ *                 upstream too) | 0 every stage
+ *   "dry_skip"    -1 auto (default): while >= 20 % of the cells are dry, tiles of 128 cells that are all dry, stored
+ *                 as (b, +0, +0) and surrounded by dry cells are skipped by the flux / draining-dt / update kernels and
+ *                 by the stores of the reconstruction | 0 off | 1 on */
 SWE_API int swe_set_option(swe_ctx *ctx, const char *key, int32_t value);
 SWE_API int swe_get_option(swe_ctx *ctx, const char *key, int32_t *value);
 /* Debug tap (taps enabled): how many cells took each branch in the last swe_compute_interface_values.

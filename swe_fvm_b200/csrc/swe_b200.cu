@@ -57,6 +57,10 @@ struct swe_ctx {
     bool k1_dry = false;        // every K1 launch since the last `begin` maintained the flags
     int64_t steps_since_eval = 0;
     unsigned char *tile_dry = nullptr, *tile_dry0 = nullptr, *tile_zero = nullptr;  // [ntiles]: this stage / saved state / all zero
+    bool flux_since_k1 = false, drain_since_k1 = false;  // a full flux / draining-dt pass ran after the last reconstruction pass
+    bool prev_flux = false, prev_drain = false;          // ... after the previous one (valid for the current pass)
+    unsigned char *tile_prev = nullptr;  // flags of the previous K1 pass (copied from tile_dry at every `begin`; tile_dry is zeroed on
+                                         // the stream whenever it stops describing what the edge-state arrays hold: graph-replay safe)
     int ntiles = 0;
     int64_t state_version = 1, flags_version = 0;  // flags valid iff equal
     bool flags0_valid = false;
@@ -179,6 +183,9 @@ static DevFields dev_fields(const swe_ctx *c) {
     s.tile_dry = c->tile_dry;
     s.td = (c->dry_active && c->flags_version == c->state_version) ? c->tile_dry : c->tile_zero;
     s.td0 = (c->dry_active && c->flags0_valid) ? c->tile_dry0 : c->tile_zero;
+    s.tdp = c->k1_dry ? c->tile_prev : c->tile_zero;
+    s.tdf = (c->k1_dry && c->prev_flux) ? c->tile_prev : c->tile_zero;
+    s.tdd = (c->k1_dry && c->prev_drain) ? c->tile_prev : c->tile_zero;
     return s;
 }
 
@@ -191,6 +198,12 @@ static inline int drain_grid(const swe_ctx *c) {
 #else
     return nblk(c->nt, kBlock * SWE_K3_ILP);
 #endif
+}
+// the tile flags stop describing what the edge-state arrays hold (state / bed set from outside, mode change): zero them
+// on the stream, so the next reconstruction pass finds no `previous` flags (works under graph replay too)
+static inline void drop_tile_flags(swe_ctx *c) {
+    if (c->tile_dry) { cudaSetDevice(c->device); cudaMemsetAsync(c->tile_dry, 0, (size_t)c->ntiles, c->stream); }
+    c->flags_version = 0;
 }
 // dry-region skipping: are the flags of this stage usable right now?
 static inline bool dry_now(const swe_ctx *c) { return c->dry_active && c->flags_version == c->state_version; }
@@ -213,7 +226,7 @@ static int dry_refresh(swe_ctx *c) {
     CUDA_TRY(c, cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const bool on = (double)h >= 0.2 * (double)c->nt;
-    if (on != c->dry_active) { c->dry_active = on; c->flags_version = 0; c->flags0_valid = false; }
+    if (on != c->dry_active) { c->dry_active = on; c->flags_version = 0; c->flags0_valid = false; drop_tile_flags(c); }
     return SWE_OK;
 }
 static int launch_check(swe_ctx *c, const char *what) {
@@ -230,7 +243,7 @@ static void destroy_ctx(swe_ctx *c) {
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->pwl, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
-                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero};
+                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero, c->tile_prev};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
@@ -623,6 +636,8 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(dalloc(&c->tile_dry, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_dry0, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_zero, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_dry, 0, (size_t)c->ntiles)); CREATE_TRY(cudaMemset(c->tile_dry0, 0, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_zero, 0, (size_t)c->ntiles));
+    CREATE_TRY(dalloc(&c->tile_prev, (size_t)c->ntiles));
+    CREATE_TRY(cudaMemset(c->tile_prev, 0, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 8));
     const double scal0[8] = {1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0};  // [0] min_len, [1] dt, [2] time, [3] running min, [4] global min_len
     CREATE_TRY(cudaMemcpy(c->scal, scal0, sizeof(scal0), cudaMemcpyHostToDevice));
@@ -684,6 +699,7 @@ SWE_API int swe_set_state_async(swe_ctx *c, const double *prim) {
     CUDA_TRY(c, cudaMemcpyAsync(c->stage_aos, prim, sizeof(double) * 3 * c->nt, cudaMemcpyHostToDevice, c->stream));
     c->state_version++;
     c->dry_eval_pending = true;
+    drop_tile_flags(c);
     k_state_in<<<nblk(c->nt, 256), 256, 0, c->stream>>>(c->nt, c->cell_old, c->stage_aos, c->cur[0], c->cur[1], c->cur[2]);
     if ((rc = launch_check(c, "k_state_in"))) return rc;
     k_set_scalar<<<1, 1, 0, c->stream>>>(c->scal + 2, 0.0);
@@ -828,7 +844,7 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "skip_cfl")) { if (value < 0 || value > 1) return bad("0 every stage rebuilds the CFL minimum, 1 only the last stage of a step"); c->opt_skip_cfl = value; }
     else if (!std::strcmp(key, "dry_skip")) {
         if (value < -1 || value > 1) return bad("-1 auto (on while >= 20 % of the cells are dry), 0 every tile is processed, 1 tiles of deep-dry cells are skipped by the flux / draining / update kernels");
-        c->opt_dry_skip = value; c->flags_version = 0; c->flags0_valid = false; c->dry_eval_pending = true;
+        c->opt_dry_skip = value; c->flags_version = 0; c->flags0_valid = false; c->dry_eval_pending = true; drop_tile_flags(c);
         if (value >= 0) c->dry_active = value == 1;
     }
     else return bad("unknown option (recon, pw2, roe_fix, cfl_abs, k1_tiled, fused_drain, skip_cfl, dry_skip, graph)");
@@ -874,7 +890,14 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         if (c->taps) CUDA_TRY(c, cudaMemsetAsync(c->dbg, 0, sizeof(unsigned long long) * BR_COUNT, c->stream));
         // dry-tile flags: preset to "deep dry", cleared by every cell that is not (off: all zero, nothing is skipped)
         c->k1_dry = c->dry_active && !c->taps && c->opt_tiled == 0;
-        if (c->k1_dry) CUDA_TRY(c, cudaMemsetAsync(c->tile_dry, 1, (size_t)c->ntiles, c->stream));
+        c->prev_flux = c->flux_since_k1; c->prev_drain = c->drain_since_k1;
+        c->flux_since_k1 = false; c->drain_since_k1 = false;
+        if (c->k1_dry) {  // the last pass's flags become `previous`, the new ones start as "deep dry"
+            CUDA_TRY(c, cudaMemcpyAsync(c->tile_prev, c->tile_dry, (size_t)c->ntiles, cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(c->tile_dry, 1, (size_t)c->ntiles, c->stream));
+        } else {          // this pass does not maintain the flags: nothing may be assumed by the next one
+            CUDA_TRY(c, cudaMemsetAsync(c->tile_dry, 0, (size_t)c->ntiles, c->stream));
+        }
         c->k1_covered = 0;
         c->flags_version = 0;
     }
@@ -932,6 +955,8 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         if ((rc = launch_check(c, "k_partwet2"))) return rc;
         // the flags describe the current state once every cell went through pass 1 (ranges may come in any order)
         if (c->k1_dry && c->k1_covered == (int64_t)c->nt) c->flags_version = c->state_version;
+        if (c->k1_dry && c->k1_covered != (int64_t)c->nt)  // partial pass: untouched tiles still carry the preset
+            CUDA_TRY(c, cudaMemsetAsync(c->tile_dry, 0, (size_t)c->ntiles, c->stream));
     }
     return SWE_OK;
 }
@@ -971,6 +996,7 @@ static int compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws, bool cfl)
     const DevFields s = dev_fields(c);
     const int kt = kt_begin(c, KT_FLUX);
     launch_flux(c, m, s, id, cfl || c->taps || !c->opt_skip_cfl);
+    c->flux_since_k1 = true;
     kt_end(c, kt);
     return launch_check(c, "k_flux");
 }
@@ -1004,6 +1030,7 @@ static int stage_drain(swe_ctx *c, double ***outb_out) {
         if (dry_now(c)) k_drain<true><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
         else k_drain<false><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
         c->dti_complete = true;
+        c->drain_since_k1 = true;
     }
     kt_end(c, kt);
     if ((rc = launch_check(c, "k_drain"))) return rc;
@@ -1446,6 +1473,7 @@ SWE_API int swe_case_set_bathymetry_device(swe_ctx *c, const swe_case *cs) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     c->state_version++;  // the bed (and with it every cell class) changes
     c->dry_eval_pending = true;
+    drop_tile_flags(c);
     k_case_bathymetry<<<nblk(c->nn, 256), 256, 0, c->stream>>>(c->nn, c->node, *cs);
     int rc;
     if ((rc = launch_check(c, "k_case_bathymetry"))) return rc;
@@ -1458,6 +1486,7 @@ SWE_API int swe_case_initial_state_device(swe_ctx *c, const swe_case *cs, int32_
     CUDA_TRY(c, cudaSetDevice(c->device));
     c->state_version++;
     c->dry_eval_pending = true;
+    drop_tile_flags(c);
     k_case_init<<<nblk(c->nt, 128), 128, 0, c->stream>>>(dev_mesh(c), *cs, quad_n, t, c->cur[0], c->cur[1], c->cur[2]);
     int rc;
     if ((rc = launch_check(c, "k_case_init"))) return rc;

@@ -50,8 +50,16 @@ struct DevFields {
     // so K2 writes zeros without reading the edge states, K3 writes 0 and K4 leaves the tile alone — bit-identical to
     // doing the work. td / td0: the flags K2-K4 may use for this stage / for the state saved by swe_save_state (an
     // all-zero array when they do not describe the current data).
+    // tdp: the flags of the PREVIOUS complete reconstruction pass (all zero when unknown). Invariant kept by K1: while a
+    // tile stays flagged from one pass to the next, the edge-side values of its cells are (0, 0, 0), their gradient is
+    // the bed slope and their class is 0 — written when the tile first became deep dry — so a deep-dry cell of a tile
+    // that was already flagged has nothing to compute or store.
     unsigned char *tile_dry;
-    const unsigned char *td, *td0;
+    const unsigned char *td, *td0, *tdp;
+    // tdf / tdd: the previous pass's flags as far as the FLUX / DRAINING-DT arrays are concerned: a tile flagged then and
+    // now already holds +0 fluxes on all its edges / dt = 0 in all its cells (written or computed after that pass), so
+    // even the zero stores are skipped. All zero unless a flux / draining pass ran after the previous reconstruction.
+    const unsigned char *tdf, *tdd;
     signed char *cls;                // [nt] 0 dry, 1 part-wet, 2 full-wet
     int *pw_list;                    // [nt] compacted ids of part-wet cells (pass 2 work list)
     int *rs_list;                    // [nt] cells left to the generic reconstruction kernel (K1s)
@@ -333,6 +341,7 @@ __device__ __forceinline__ bool fast_compute(const DevFields &s, const int nt, c
         const bool nb_dry = ((wall & 1) || !is_wet(N00 - G0.z)) && ((wall & 2) || !is_wet(N10 - G1.z)) &&
                             ((wall & 4) || !is_wet(N20 - G2.z));
         if (!(canon && nb_dry)) s.tile_dry[i >> kUpdTileShift] = 0;
+        else if (__ldg(s.tdp + (i >> kUpdTileShift))) return true;  // outputs already in place (see DevFields::tdp)
     }
     const bool full = !bnd && (smax(smax(P0.z, P1.z), P2.z) < w);
     const bool nbfull = (G0.w < N00) && (G1.w < N10) && (G2.w < N20);
@@ -795,10 +804,19 @@ __device__ __forceinline__ int slot_cell(int slot, int nt) {
     if (i >= nt) i -= nt;
     return i;
 }
-__device__ __forceinline__ bool edge_in_dry_tile(const unsigned char *td, int nt, int sl, int sr) {
-    unsigned f = __ldg(td + (slot_cell(sl, nt) >> kUpdTileShift));
-    if (sr >= 0) f |= __ldg(td + (slot_cell(sr, nt) >> kUpdTileShift));
-    return f != 0;
+// 0: compute the edge; 1: a cell of a deep-dry tile on either side, the flux is +0; 2: ... and that tile was already
+// flagged in the previous pass, the flux arrays hold +0 for this edge
+__device__ __forceinline__ int edge_in_dry_tile(const unsigned char *td, const unsigned char *tdf, int nt, int sl, int sr) {
+    const int tl = slot_cell(sl, nt) >> kUpdTileShift;
+    unsigned f = __ldg(td + tl);
+    unsigned g = f & __ldg(tdf + tl);
+    if (sr >= 0) {
+        const int tr = slot_cell(sr, nt) >> kUpdTileShift;
+        const unsigned fr = __ldg(td + tr);
+        f |= fr;
+        g |= fr & __ldg(tdf + tr);
+    }
+    return g ? 2 : (f ? 1 : 0);
 }
 #ifndef SWE_K2_GRID_PER_SM
 #define SWE_K2_GRID_PER_SM 64  // A/B at 64M cells: 16 -> 2.114 ms, 64 -> 2.062 ms, one block per 128 edges -> 2.889 ms
@@ -846,12 +864,12 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
         int nx = e + stride;
         int nsl = 0, nsr = 0;
         if (nx < ne) { nsl = __ldg(m.slotL + nx); nsr = __ldg(m.slotR + nx); }
-        bool skip = edge_in_dry_tile(s.td, m.nt, sl, sr);
+        int skip = edge_in_dry_tile(s.td, s.tdf, m.nt, sl, sr);
         for (;;) {
             const int n2 = nx + stride;
             int n2sl = 0, n2sr = 0;
             if (n2 < ne) { n2sl = __ldg(m.slotL + n2); n2sr = __ldg(m.slotR + n2); }
-            const bool nskip = (nx < ne) && edge_in_dry_tile(s.td, m.nt, nsl, nsr);
+            const int nskip = (nx < ne) ? edge_in_dry_tile(s.td, s.tdf, m.nt, nsl, nsr) : 0;
             double f0, f1, f2;
             if (skip) {  // a cell of a deep-dry tile on either side: both cells are dry, the flux is exactly +0
                 f0 = 0.; f1 = 0.; f2 = 0.;
@@ -869,7 +887,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K2_MIN_BLOCKS) k_flux(DevMesh m, D
                     if (CFL) l2w = (cand < l2w) ? cand : l2w;
                 }
             }
-            st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2);
+            if (skip != 2) { st_once(s.f0 + e, f0); st_once(s.f1 + e, f1); st_once(s.f2 + e, f2); }
             if (nx >= ne) break;
             e = nx; nx = n2; sl = nsl; sr = nsr; nsl = n2sl; nsr = n2sr; skip = nskip;
         }
@@ -945,9 +963,11 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
         const unsigned dry_a = __ldg(s.td + (i0 >> kUpdTileShift)), dry_b = __ldg(s.td + (j1 >> kUpdTileShift));
         a0 = ldg_i32_early(m.te + i0); a1 = ldg_i32_early(m.te + nt + i0); a2 = ldg_i32_early(m.te + 2 * nt + i0);
         b0 = ldg_i32_early(m.te + j1); b1 = ldg_i32_early(m.te + nt + j1); b2 = ldg_i32_early(m.te + 2 * nt + j1);
-        if (dry_a && dry_b) {  // deep-dry tiles: dry cells, draining dt = 0
-            st_once(s.dti + i0, 0.);
-            if (two) st_once(s.dti + i1, 0.);
+        if (dry_a && dry_b) {  // deep-dry tiles: dry cells, draining dt = 0 (already stored if the tiles were flagged before)
+            if (!(__ldg(s.tdd + (i0 >> kUpdTileShift)) && __ldg(s.tdd + (j1 >> kUpdTileShift)))) {
+                st_once(s.dti + i0, 0.);
+                if (two) st_once(s.dti + i1, 0.);
+            }
             return;
         }
     } else {
@@ -1048,13 +1068,17 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     const bool active = FUSED ? (i >= first && i < last) : true;
     if (!FUSED) { if (i >= last) return; }
     else if (!active) i = first;  // idle lanes of a partial tile shadow a valid cell (loads stay in bounds), never store
-    // dry-tile flags: loaded together with the cell's own (coalesced) data, tested before the gathers, so a wet tile
-    // pays no extra memory round trip and a deep-dry tile skips the edge / neighbour gathers
-    unsigned skip_t = 0;
+    // dry-region form: the tile flag is tested before anything else is loaded. A deep-dry tile (now and, when U0 enters
+    // the combination, at swe_save_state) costs one byte per cell: its cells stay (cb, +0, +0). A wet tile pays one extra
+    // memory round trip (+8 % measured), which is why this instantiation is only used while >= 20 % of the cells are dry.
     if (DRY) {
         const int t = i >> kUpdTileShift;
-        skip_t = __ldg(s.td + t);
+        unsigned skip_t = __ldg(s.td + t);
         if (!PLAIN) skip_t &= __ldg(s.td0 + t);
+        if (skip_t) {
+            if (wout != s.w) { wout[i] = __ldg(m.cb + i); uout[i] = 0.; vout[i] = 0.; }  // out of place (first stage after swe_save_state)
+            return;
+        }
     }
     // All loads are issued before any arithmetic (ids -> gathers: two dependent round trips, every
     // gather of the cell in flight at once). Written out explicitly because the compiler's own
@@ -1062,10 +1086,7 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     // when an unrelated kernel parameter changed.
     int te[3], tn[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (DRY) { te[k] = ldg_i32_early(m.te + k * nt + i); tn[k] = ldg_i32_early(m.tt + k * nt + i); }
-        else { te[k] = __ldg(m.te + k * nt + i); tn[k] = __ldg(m.tt + k * nt + i); }
-    }
+    for (int k = 0; k < 3; ++k) { te[k] = __ldg(m.te + k * nt + i); tn[k] = __ldg(m.tt + k * nt + i); }
     // dt_coef != 0: stage dt = dt_coef * (device-resident dt), else the host value
     const double dt = (dt_coef != 0.) ? dt_coef * s.scal[1] : dt_host;
     const double cb = __ldg(m.cb + i);
@@ -1075,11 +1096,6 @@ __global__ void __launch_bounds__(kBlock, SWE_K4_MIN_BLOCKS) k_update(DevMesh m,
     const double wc = s.w[i], uc = s.u[i], vc = s.v[i];
     double wa = 0., ua = 0., va = 0.;
     if (!PLAIN) { wa = w0[i]; ua = u0[i]; va = v0[i]; }
-    if (DRY && skip_t) {
-        // deep-dry tile now (and, when U0 enters the combination, at swe_save_state): the cell stays (cb, +0, +0)
-        if (wout != s.w) { wout[i] = cb; uout[i] = 0.; vout[i] = 0.; }  // out of place (first stage after swe_save_state)
-        return;
-    }
     double F0[3], F1[3], F2[3], dtn[3], len[3], hek[3], cu[3], cv[3];
     double2 nrm[3];
     const int lo_t = max(base, first), hi_t = min(base + kBlock, last);  // FUSED: cells whose dti this block computes
