@@ -68,16 +68,30 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "timestamp")
 
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self, which: str):
+        """Wall-clock bounds of the timed region: the sampler is started BEFORE the warm-up (nvidia-smi needs a few hundred
+        milliseconds to come up, longer than a short timed region) and only the samples stamped inside the region count."""
+        setattr(self, "t_" + which, time.time())
+
+    @staticmethod
+    def _stamp(txt: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         if self.p is None:
@@ -90,16 +104,27 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+                rows.append((self._stamp(c[9]), float(c[1]), float(c[2]), float(c[3]), c[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+        t0, t1 = getattr(self, "t_begin", None), getattr(self, "t_end", None)
+        inside = [r for r in rows if r[0] is not None and t0 is not None and t1 is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        if not inside and rows and t0 is not None and t1 is not None:  # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (t0 + t1)
+            near = sorted((r for r in rows if r[0] is not None), key=lambda r: abs(r[0] - mid))[:2]
+            inside = [r for r in near if abs(r[0] - mid) <= 0.5 * (t1 - t0) + 0.25]
+        if t0 is None:
+            inside = rows
+        sm, mx, pw, reasons = [], [], [], set()
+        for _, a, b, p_, flags in inside:
+            sm.append(a); mx.append(b); pw.append(p_)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         try:
@@ -368,17 +393,21 @@ def run_gpu(args):
         barrier()
         return ev0.elapsed_time(ev1)
 
-    # prime the CFL dt with one tiny step, then warm up
+    # prime the CFL dt with one tiny step, then warm up (the clock sampler starts here so that it is up in time)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     run_steps(1); sync()
     dt_first[0] = cfl()
     run_steps(max(args.warmup, 1)); sync()
     dt_first[0] = cfl()
 
     # ---- timed region: K steps, state resident in HBM ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     sd.kernel_timing(True)
     launches0 = sd.launch_count()
+    if sampler:
+        sampler.mark("begin")
     ms = timed(args.steps)
+    if sampler:
+        sampler.mark("end")
     clocks = sampler.stop() if sampler else None
     launches = sd.launch_count() - launches0
     ktimes = sd.kernel_times()
@@ -552,7 +581,7 @@ def main():
                     help="strong scaling: fixed global mesh of global_n x global_n squares split over the GPUs "
                          "(configs[4]: 8192 = 268M cells)")
     ap.add_argument("--case", default="fully_wet", choices=["fully_wet", "thacker"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20, help="steps of the host-buffer pipeline (its fill and drain are inside the timed region)")
     ap.add_argument("--cpu-n", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
