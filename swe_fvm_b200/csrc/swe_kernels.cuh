@@ -438,7 +438,20 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(Dev
             nt0 = __ldg(m.tt + nx); nt1 = __ldg(m.tt + nt + nx); nt2 = __ldg(m.tt + 2 * nt + nx);
         }
 #if SWE_K1_SPLIT
-        if (!reconstruct_cell_fast<TAPS, RECON, DRY>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
+        bool done = false;
+        if (DRY && __ldg(s.tdp + (i >> kUpdTileShift))) {
+            // The tile was deep dry in the previous pass, so this cell most likely still is: decide that from the cell's
+            // own state and its neighbours' depths alone (56 instead of 96 bytes per cell, no node / geometry packets).
+            // Then nothing has to be computed or stored (DevFields::tdp) and the tile flag keeps its preset.
+            const double cb = __ldg(m.cb + i);
+            const double w = __ldg(s.w + i), u = __ldg(s.u + i), v = __ldg(s.v + i);
+            const int j0 = max(it0, 0), j1 = max(it1, 0), j2 = max(it2, 0);
+            const double h0 = __ldg(s.w + j0) - __ldg(m.cb + j0), h1 = __ldg(s.w + j1) - __ldg(m.cb + j1),
+                         h2 = __ldg(s.w + j2) - __ldg(m.cb + j2);
+            done = __double_as_longlong(w) == __double_as_longlong(cb) && __double_as_longlong(u) == 0ll &&
+                   __double_as_longlong(v) == 0ll && (it0 < 0 || !is_wet(h0)) && (it1 < 0 || !is_wet(h1)) && (it2 < 0 || !is_wet(h2));
+        }
+        if (!done && !reconstruct_cell_fast<TAPS, RECON, DRY>(m, s, i, ip0, ip1, ip2, it0, it1, it2)) s.rs_list[atomicAdd(&s.flags[4], 1)] = i;
 #else
         reconstruct_cell<TAPS>(m, s, i, ip0, ip1, ip2, it0, it1, it2);
 #endif
