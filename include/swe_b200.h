@@ -206,7 +206,9 @@ SWE_API int swe_set_fluxer(swe_ctx *ctx, int32_t id);
  *                 upstream too) | 0 every stage
  *   "dry_skip"    -1 auto (default): while >= 20 % of the cells are dry, tiles of 128 cells that are all dry, stored
  *                 as (b, +0, +0) and surrounded by dry cells are skipped by the flux / draining-dt / update kernels and
- *                 by the stores of the reconstruction | 0 off | 1 on */
+ *                 by the stores of the reconstruction | 0 off | 1 on
+ *   "dry_list"    -1 auto: on meshes of >= 4M cells the dry-region stage update runs over a compacted list of the tiles
+ *                 it has to process | 0 every block tests its own tile flag | 1 always the list */
 SWE_API int swe_set_option(swe_ctx *ctx, const char *key, int32_t value);
 SWE_API int swe_get_option(swe_ctx *ctx, const char *key, int32_t *value);
 /* Debug tap (taps enabled): how many cells took each branch in the last swe_compute_interface_values.

@@ -59,6 +59,8 @@ struct swe_ctx {
     unsigned char *tile_dry = nullptr, *tile_dry0 = nullptr, *tile_zero = nullptr;  // [ntiles]: this stage / saved state / all zero
     bool flux_since_k1 = false, drain_since_k1 = false;  // a full flux / draining-dt pass ran after the last reconstruction pass
     bool prev_flux = false, prev_drain = false;          // ... after the previous one (valid for the current pass)
+    int *tile_list = nullptr;            // [1 + ntiles] compacted tiles of the dry-region stage update
+    int opt_dry_list = -1;               // -1 auto (meshes of >= 4M cells), 0 every block tests its own flag, 1 always the list
     unsigned char *tile_prev = nullptr;  // flags of the previous K1 pass (copied from tile_dry at every `begin`; tile_dry is zeroed on
                                          // the stream whenever it stops describing what the edge-state arrays hold: graph-replay safe)
     int ntiles = 0;
@@ -164,6 +166,9 @@ using swe::host_threads;
 
 static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
 
+// the compacted tile list of the dry-region stage update costs three small launches per stage: only worth it on big meshes
+constexpr int kTileListMinCells = 1 << 22;
+static inline bool use_tile_list(const swe_ctx *c) { return c->opt_dry_list < 0 ? c->nt >= kTileListMinCells : c->opt_dry_list == 1; }
 static DevMesh dev_mesh(const swe_ctx *c) {
     DevMesh m;
     m.nt = c->nt; m.ne = c->ne; m.nn = c->nn;
@@ -183,6 +188,7 @@ static DevFields dev_fields(const swe_ctx *c) {
     s.tile_dry = c->tile_dry;
     s.td = (c->dry_active && c->flags_version == c->state_version) ? c->tile_dry : c->tile_zero;
     s.td0 = (c->dry_active && c->flags0_valid) ? c->tile_dry0 : c->tile_zero;
+    s.tile_list = use_tile_list(c) ? c->tile_list : nullptr;
     s.tdp = c->k1_dry ? c->tile_prev : c->tile_zero;
     s.tdf = (c->k1_dry && c->prev_flux) ? c->tile_prev : c->tile_zero;
     s.tdd = (c->k1_dry && c->prev_drain) ? c->tile_prev : c->tile_zero;
@@ -243,7 +249,7 @@ static void destroy_ctx(swe_ctx *c) {
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->pwl, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
-                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero, c->tile_prev};
+                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero, c->tile_prev, c->tile_list};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
@@ -327,7 +333,7 @@ static void preload_kernels() {
     SWE_LOAD(k_reconstruct_slow<T>); SWE_LOAD(k_partwet2<T>)
     SWE_LOAD_K1(false); SWE_LOAD_K1(true);
     SWE_LOAD(k_reconstruct<false, 0, true>); SWE_LOAD(k_reconstruct<false, 1, true>); SWE_LOAD(k_reconstruct<false, 2, true>);
-    SWE_LOAD(k_drain<true>); SWE_LOAD(k_count_dry);
+    SWE_LOAD(k_drain<true>); SWE_LOAD(k_count_dry); SWE_LOAD(k_tile_compact); SWE_LOAD(k_fill_dry_tiles);
     SWE_LOAD(k_update<true, true, false, false, true>); SWE_LOAD(k_update<true, false, false, false, true>);
     SWE_LOAD(k_update<false, true, false, false, true>); SWE_LOAD(k_update<false, false, false, false, true>);
 #define SWE_X(ID, NAME, TYPE) SWE_LOAD(k_flux<TYPE, false>); SWE_LOAD(k_flux<TYPE, true>); \
@@ -636,6 +642,8 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(dalloc(&c->tile_dry, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_dry0, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_zero, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_dry, 0, (size_t)c->ntiles)); CREATE_TRY(cudaMemset(c->tile_dry0, 0, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_zero, 0, (size_t)c->ntiles));
+    CREATE_TRY(dalloc(&c->tile_list, (size_t)c->ntiles + 1));
+    CREATE_TRY(cudaMemset(c->tile_list, 0, sizeof(int) * ((size_t)c->ntiles + 1)));
     CREATE_TRY(dalloc(&c->tile_prev, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_prev, 0, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->flags, 0, sizeof(int) * 8));
@@ -842,6 +850,7 @@ SWE_API int swe_set_option(swe_ctx *c, const char *key, int32_t value) {
     else if (!std::strcmp(key, "k1_tiled")) { if (value < 0 || value > 2 * SWE_K1_TILED) return bad("0 gather kernel, 1 TMA-staged shared-memory tiles, 2 cp.async software pipeline"); c->opt_tiled = value; }
     else if (!std::strcmp(key, "fused_drain")) { if (value < 0 || value > 1) return bad("0 separate k_drain pass, 1 draining dt fused into the stage update"); c->opt_fused_drain = value; }
     else if (!std::strcmp(key, "skip_cfl")) { if (value < 0 || value > 1) return bad("0 every stage rebuilds the CFL minimum, 1 only the last stage of a step"); c->opt_skip_cfl = value; }
+    else if (!std::strcmp(key, "dry_list")) { if (value < -1 || value > 1) return bad("-1 auto (>= 4M cells), 0 every block of the dry-region update tests its own tile flag, 1 compacted tile list"); c->opt_dry_list = value; }
     else if (!std::strcmp(key, "dry_skip")) {
         if (value < -1 || value > 1) return bad("-1 auto (on while >= 20 % of the cells are dry), 0 every tile is processed, 1 tiles of deep-dry cells are skipped by the flux / draining / update kernels");
         c->opt_dry_skip = value; c->flags_version = 0; c->flags0_valid = false; c->dry_eval_pending = true; drop_tile_flags(c);
@@ -859,6 +868,7 @@ SWE_API int swe_get_option(swe_ctx *c, const char *key, int32_t *value) {
     else if (!std::strcmp(key, "k1_tiled")) *value = c->opt_tiled;
     else if (!std::strcmp(key, "fused_drain")) *value = c->opt_fused_drain;
     else if (!std::strcmp(key, "skip_cfl")) *value = c->opt_skip_cfl;
+    else if (!std::strcmp(key, "dry_list")) *value = c->opt_dry_list;
     else if (!std::strcmp(key, "dry_skip")) *value = c->opt_dry_skip;
     else if (!std::strcmp(key, "graph")) *value = c->opt_graph;
     else { c->err = std::string("swe_get_option: unknown option ") + key; return SWE_ERR_INVALID; }
@@ -1053,10 +1063,19 @@ static int stage_update_range(swe_ctx *c, double **outb, double a0, double a1, d
     const int g = fused ? ((last - 1) >> kUpdTileShift) - (first >> kUpdTileShift) + 1 : nblk(last - first, kBlock);
     const int kt = kt_begin(c, KT_UPDATE);
     const bool cor_on = c->cor != 0.;
+    const bool listed = use_tile_list(c);
+    const int g_dry = listed ? c->ntiles : g;  // listed form: one block per listed tile, the count lives on the device
+    if (dry && !fused && listed) {
+        const int use_td0 = a0 == 0. ? 0 : 1;
+        CUDA_TRY(c, cudaMemsetAsync(c->tile_list, 0, sizeof(int), c->stream));
+        k_tile_compact<<<nblk(c->ntiles, 256), 256, 0, c->stream>>>(c->ntiles, s.td, s.td0, use_td0, c->tile_list);
+        if (outb[0] != s.w)  // out of place (first stage after swe_save_state): the skipped tiles keep (cb, +0, +0)
+            k_fill_dry_tiles<<<nblk(last - first, 256), 256, 0, c->stream>>>(first, last, s.td, s.td0, use_td0, c->cb, outb[0], outb[1], outb[2]);
+    }
 #define SWE_UPD(PLAIN, COR, W0, U0, V0) \
     do { \
         if (fused) k_update<PLAIN, COR, false, true><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
-        else if (dry) k_update<PLAIN, COR, false, false, true><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
+        else if (dry) k_update<PLAIN, COR, false, false, true><<<g_dry, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
         else k_update<PLAIN, COR><<<g, kBlock, 0, c->stream>>>(m, s, W0, U0, V0, outb[0], outb[1], outb[2], a0, a1, dt_host, dt_coef, c->cor, first, last); \
     } while (0)
     if (a0 == 0.) {
@@ -1161,7 +1180,7 @@ static int run_graphed(swe_ctx *c, swe_scheme scheme, swe_flux flux, swe_wavespe
         return code;
     };
     const int fluxer = c->fluxer >= 0 ? c->fluxer : 3 * (int)flux + (int)ws;
-    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7) | (c->opt_skip_cfl << 10) | ((c->dry_active ? 1 : 0) << 11);
+    const int opts = c->opt_recon | (c->opt_pw2 << 2) | (c->opt_roe_fix << 3) | (c->opt_cfl_abs << 4) | (c->opt_tiled << 8) | ((c->taps ? 1 : 0) << 6) | (c->opt_fused_drain << 7) | (c->opt_skip_cfl << 10) | ((c->dry_active ? 1 : 0) << 11) | ((use_tile_list(c) ? 1 : 0) << 12);
     for (int64_t s = 0; s < nsteps; ++s) {
         const int parity = (c->cur == c->bufA) ? 0 : 1;
         swe_ctx::StepGraph *g = nullptr;

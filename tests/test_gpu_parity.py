@@ -427,10 +427,11 @@ def test_dry_region_skipping_is_bit_identical(scheme, reorder):
     ref = Oracle(mesh, cor=0.05)
     ref.set_state(v0)
     runs = []
-    for skip, graph in ((1, 0), (0, 0), (1, 1)):
+    for skip, graph, dlist in ((1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1)):
         sd = SpaceDisc("hllc", "einfeldt", mesh, v0, cor=0.05, reorder=reorder)
         sd.set_option("dry_skip", skip)
         sd.set_option("graph", graph)
+        sd.set_option("dry_list", dlist)  # 1: the stage update runs over the compacted list of tiles (the form big meshes use)
         assert sd.get_option("dry_skip") == skip
         runs.append((sd, TimeDisc(sd)))
     sc = SCHEMES[scheme]
