@@ -57,8 +57,9 @@ struct swe_ctx {
     bool k1_dry = false;        // every K1 launch since the last `begin` maintained the flags
     int64_t steps_since_eval = 0;
     unsigned char *tile_dry = nullptr, *tile_dry0 = nullptr, *tile_zero = nullptr;  // [ntiles]: this stage / saved state / all zero
-    bool flux_since_k1 = false, drain_since_k1 = false;  // a full flux / draining-dt pass ran after the last reconstruction pass
-    bool prev_flux = false, prev_drain = false;          // ... after the previous one (valid for the current pass)
+    // flags of the last pass whose flux / draining-dt kernel ran with them: tile flagged there => its edges hold +0 fluxes /
+    // its cells hold dt = 0 in memory (copied on the stream right after those kernels, zeroed when they run without flags)
+    unsigned char *tile_fluxed = nullptr, *tile_drained = nullptr;
     int *tile_list = nullptr;            // [1 + ntiles] compacted tiles of the dry-region stage update
     int opt_dry_list = -1;               // -1 auto (meshes of >= 4M cells), 0 every block tests its own flag, 1 always the list
     unsigned char *tile_prev = nullptr;  // flags of the previous K1 pass (copied from tile_dry at every `begin`; tile_dry is zeroed on
@@ -190,8 +191,8 @@ static DevFields dev_fields(const swe_ctx *c) {
     s.td0 = (c->dry_active && c->flags0_valid) ? c->tile_dry0 : c->tile_zero;
     s.tile_list = use_tile_list(c) ? c->tile_list : nullptr;
     s.tdp = c->k1_dry ? c->tile_prev : c->tile_zero;
-    s.tdf = (c->k1_dry && c->prev_flux) ? c->tile_prev : c->tile_zero;
-    s.tdd = (c->k1_dry && c->prev_drain) ? c->tile_prev : c->tile_zero;
+    s.tdf = c->tile_fluxed;
+    s.tdd = c->tile_drained;
     return s;
 }
 
@@ -208,7 +209,12 @@ static inline int drain_grid(const swe_ctx *c) {
 // the tile flags stop describing what the edge-state arrays hold (state / bed set from outside, mode change): zero them
 // on the stream, so the next reconstruction pass finds no `previous` flags (works under graph replay too)
 static inline void drop_tile_flags(swe_ctx *c) {
-    if (c->tile_dry) { cudaSetDevice(c->device); cudaMemsetAsync(c->tile_dry, 0, (size_t)c->ntiles, c->stream); }
+    if (c->tile_dry) {
+        cudaSetDevice(c->device);
+        cudaMemsetAsync(c->tile_dry, 0, (size_t)c->ntiles, c->stream);
+        cudaMemsetAsync(c->tile_fluxed, 0, (size_t)c->ntiles, c->stream);
+        cudaMemsetAsync(c->tile_drained, 0, (size_t)c->ntiles, c->stream);
+    }
     c->flags_version = 0;
 }
 // dry-region skipping: are the flags of this stage usable right now?
@@ -249,7 +255,7 @@ static void destroy_ctx(swe_ctx *c) {
                     c->n2c_start, c->n2c_cells, c->cfl_mask, c->dmin0, c->cell_old, c->edge_old, c->node_old, c->bufA[0],
                     c->bufA[1], c->bufA[2], c->bufB[0], c->bufB[1], c->bufB[2], c->ceh, c->ceu, c->cev, c->cgx, c->cgy,
                     c->cew, c->f0, c->f1, c->f2, c->dti, c->pwl, c->cls, c->pw_list, c->rs_list, c->scal, c->flags, c->diag, c->stage_aos,
-                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero, c->tile_prev, c->tile_list};
+                    c->send_cells, c->recv_cells, c->dbg, c->drain_list, c->tile_dry, c->tile_dry0, c->tile_zero, c->tile_prev, c->tile_list, c->tile_fluxed, c->tile_drained};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : c->p2p_imported) cudaIpcCloseMemHandle(p);
     if (c->p2p_recv[0]) cudaFree(c->p2p_recv[0]);
@@ -642,6 +648,8 @@ SWE_API int swe_create_classes(swe_ctx **out, const swe_mesh *mesh, int device, 
     CREATE_TRY(dalloc(&c->tile_dry, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_dry0, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_zero, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_dry, 0, (size_t)c->ntiles)); CREATE_TRY(cudaMemset(c->tile_dry0, 0, (size_t)c->ntiles));
     CREATE_TRY(cudaMemset(c->tile_zero, 0, (size_t)c->ntiles));
+    CREATE_TRY(dalloc(&c->tile_fluxed, (size_t)c->ntiles)); CREATE_TRY(dalloc(&c->tile_drained, (size_t)c->ntiles));
+    CREATE_TRY(cudaMemset(c->tile_fluxed, 0, (size_t)c->ntiles)); CREATE_TRY(cudaMemset(c->tile_drained, 0, (size_t)c->ntiles));
     CREATE_TRY(dalloc(&c->tile_list, (size_t)c->ntiles + 1));
     CREATE_TRY(cudaMemset(c->tile_list, 0, sizeof(int) * ((size_t)c->ntiles + 1)));
     CREATE_TRY(dalloc(&c->tile_prev, (size_t)c->ntiles));
@@ -900,8 +908,6 @@ static int interface_values_range(swe_ctx *c, int first, int last, bool begin, b
         if (c->taps) CUDA_TRY(c, cudaMemsetAsync(c->dbg, 0, sizeof(unsigned long long) * BR_COUNT, c->stream));
         // dry-tile flags: preset to "deep dry", cleared by every cell that is not (off: all zero, nothing is skipped)
         c->k1_dry = c->dry_active && !c->taps && c->opt_tiled == 0;
-        c->prev_flux = c->flux_since_k1; c->prev_drain = c->drain_since_k1;
-        c->flux_since_k1 = false; c->drain_since_k1 = false;
         if (c->k1_dry) {  // the last pass's flags become `previous`, the new ones start as "deep dry"
             CUDA_TRY(c, cudaMemcpyAsync(c->tile_prev, c->tile_dry, (size_t)c->ntiles, cudaMemcpyDeviceToDevice, c->stream));
             CUDA_TRY(c, cudaMemsetAsync(c->tile_dry, 1, (size_t)c->ntiles, c->stream));
@@ -1006,7 +1012,8 @@ static int compute_fluxes(swe_ctx *c, swe_flux flux, swe_wavespeed ws, bool cfl)
     const DevFields s = dev_fields(c);
     const int kt = kt_begin(c, KT_FLUX);
     launch_flux(c, m, s, id, cfl || c->taps || !c->opt_skip_cfl);
-    c->flux_since_k1 = true;
+    if (dry_now(c)) CUDA_TRY(c, cudaMemcpyAsync(c->tile_fluxed, c->tile_dry, (size_t)c->ntiles, cudaMemcpyDeviceToDevice, c->stream));
+    else if (c->dry_active) CUDA_TRY(c, cudaMemsetAsync(c->tile_fluxed, 0, (size_t)c->ntiles, c->stream));
     kt_end(c, kt);
     return launch_check(c, "k_flux");
 }
@@ -1040,7 +1047,8 @@ static int stage_drain(swe_ctx *c, double ***outb_out) {
         if (dry_now(c)) k_drain<true><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
         else k_drain<false><<<drain_grid(c), kBlock, 0, c->stream>>>(m, s);
         c->dti_complete = true;
-        c->drain_since_k1 = true;
+        if (dry_now(c)) CUDA_TRY(c, cudaMemcpyAsync(c->tile_drained, c->tile_dry, (size_t)c->ntiles, cudaMemcpyDeviceToDevice, c->stream));
+        else if (c->dry_active) CUDA_TRY(c, cudaMemsetAsync(c->tile_drained, 0, (size_t)c->ntiles, c->stream));
     }
     kt_end(c, kt);
     if ((rc = launch_check(c, "k_drain"))) return rc;
