@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(kK1Block, SWE_K1_MIN_BLOCKS) k_reconstruct(Dev
 }
 
 // ---------------------------------------------------------------------------------------
-// K1, tiled form (SWE_K1_TILED, the default): the block's cell patch is staged in shared memory.
+// K1, tiled form (option k1_tiled = 1; compiled in with SWE_K1_TILED, NOT the default: measured slower than the gather
+// kernel, profiles/r2_k1_forms_ncu.csv): the block's cell patch is staged in shared memory.
 // Cells are numbered along a Hilbert curve, so a tile of kTile consecutive cells is a compact patch
 // and ~94-96 % of its neighbour references fall inside the tile itself (measured on the structured
 // and the Gmsh meshes). Per tile one thread issues 1-D TMA bulk copies (cp.async.bulk -> mbarrier
