@@ -808,13 +808,6 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
-// read-only int32 load that the compiler may not sink below a later branch (asm volatile): used where a load must be
-// in flight BEFORE a dry-tile test so that wet tiles do not pay an extra memory round trip for the test
-__device__ __forceinline__ int ldg_i32_early(const int *p) {
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));  // volatile at the PTX level too: ptxas keeps program order
-    return v;
-}
 // cell of a cell-major slot (slot = k * nt + i, k in 0..2) and the dry-tile test of an edge (see DevFields::tile_dry)
 __device__ __forceinline__ int slot_cell(int slot, int nt) {
     int i = slot;
@@ -975,23 +968,20 @@ __global__ void __launch_bounds__(kBlock) k_drain(DevMesh m, DevFields s) {
     if (i0 >= nt) return;
     const bool two = i1 < nt;
     const int j1 = two ? i1 : i0;
-    int a0, a1, a2, b0, b1, b2;
     if (DRY) {
-        // the dry-tile flags travel with the edge ids (no extra round trip for wet tiles); tested before the flux gathers
-        const unsigned dry_a = __ldg(s.td + (i0 >> kUpdTileShift)), dry_b = __ldg(s.td + (j1 >> kUpdTileShift));
-        a0 = ldg_i32_early(m.te + i0); a1 = ldg_i32_early(m.te + nt + i0); a2 = ldg_i32_early(m.te + 2 * nt + i0);
-        b0 = ldg_i32_early(m.te + j1); b1 = ldg_i32_early(m.te + nt + j1); b2 = ldg_i32_early(m.te + 2 * nt + j1);
-        if (dry_a && dry_b) {  // deep-dry tiles: dry cells, draining dt = 0 (already stored if the tiles were flagged before)
-            if (!(__ldg(s.tdd + (i0 >> kUpdTileShift)) && __ldg(s.tdd + (j1 >> kUpdTileShift)))) {
+        // dry-region form: the tile flags are tested before anything else is loaded (like the stage update: a wet tile pays
+        // one extra memory round trip, a deep-dry tile costs two bytes per thread)
+        const int ta = i0 >> kUpdTileShift, tb = j1 >> kUpdTileShift;
+        if (__ldg(s.td + ta) && __ldg(s.td + tb)) {  // dry cells: draining dt = 0 (already stored if the tiles were flagged before)
+            if (!(__ldg(s.tdd + ta) && __ldg(s.tdd + tb))) {
                 st_once(s.dti + i0, 0.);
                 if (two) st_once(s.dti + i1, 0.);
             }
             return;
         }
-    } else {
-        a0 = __ldg(m.te + i0); a1 = __ldg(m.te + nt + i0); a2 = __ldg(m.te + 2 * nt + i0);
-        b0 = __ldg(m.te + j1); b1 = __ldg(m.te + nt + j1); b2 = __ldg(m.te + 2 * nt + j1);
     }
+    const int a0 = __ldg(m.te + i0), a1 = __ldg(m.te + nt + i0), a2 = __ldg(m.te + 2 * nt + i0);
+    const int b0 = __ldg(m.te + j1), b1 = __ldg(m.te + nt + j1), b2 = __ldg(m.te + 2 * nt + j1);
     const double ha = s.w[i0] - m.cb[i0], hb = s.w[j1] - m.cb[j1];
     const double aa = m.area[i0], ab = m.area[j1];
     const double fa0 = s.f0[a0 >= 0 ? a0 : ~a0], fa1 = s.f0[a1 >= 0 ? a1 : ~a1], fa2 = s.f0[a2 >= 0 ? a2 : ~a2];
